@@ -76,8 +76,23 @@ def backbone_block_specs():
     return specs
 
 
-def _raw_state_dict(seed: int) -> dict:
+def _raw_state_dict(seed: int, parts=("detector", "heads", "lm")) -> dict:
     sd = {}
+    if "detector" in parts:
+        _raw_detector(sd, seed)
+    if "heads" in parts:
+        _raw_heads(sd, seed)
+    if "lm" in parts:
+        _raw_lm(sd, seed)
+    return sd
+
+
+def make_partial_state_dict(seed: int = 0, parts=("heads", "lm")) -> dict:
+    """RNG-only subsets (no BN calibration): bit-identical on every host.  "detector" here is uncalibrated."""
+    return _raw_state_dict(seed, parts)
+
+
+def _raw_detector(sd, seed):
     bb = "object_detector.backbone"
     _conv_bn(sd, bb + ".0", bb + ".1", 64, 1, 7, seed)
     for prefix, cin, width, cout, stride, has_ds in backbone_block_specs():
@@ -99,12 +114,18 @@ def _raw_state_dict(seed: int) -> dict:
     _linear(sd, rh + ".box_predictor.cls_score", 30, 1024, seed)
     _linear(sd, rh + ".box_predictor.bbox_pred", 120, 1024, seed)
     _linear(sd, rh + ".dim_reduction", 1024, 2048, seed)
+
+
+def _raw_heads(sd, seed):
     for head in ("binary_classifier_region_selection", "binary_classifier_region_abnormal"):
         _linear(sd, head + ".classifier.0", 512, 1024, seed)
         _linear(sd, head + ".classifier.2", 128, 512, seed)
         _linear(sd, head + ".classifier.4", 1, 128, seed)
         sd[head + ".loss_fn.pos_weight"] = torch.tensor([2.2 if "selection" in head else 6.0])
     sd["binary_classifier_region_selection.classifier.4.bias"] += 2.0
+
+
+def _raw_lm(sd, seed):
     lm = "language_model"
     sd[lm + ".wte.weight"] = _normal(lm + ".wte.weight", (VOCAB, D_MODEL), 0.02, seed)
     sd[lm + ".wpe.weight"] = _normal(lm + ".wpe.weight", (1024, D_MODEL), 0.02, seed)  # dead weight (F3)
@@ -127,7 +148,6 @@ def _raw_state_dict(seed: int) -> dict:
     sd[lm + ".final_layernorm.bias"] = _normal(lm + ".final_layernorm.bias", (D_MODEL,), 0.02, seed)
     _linear(sd, lm + ".feature_space_transformation_nn.0", D_MODEL, D_MODEL, seed)
     _linear(sd, lm + ".feature_space_transformation_nn.2", D_MODEL, D_MODEL, seed)
-    return sd
 
 
 def _calibration_images(n=4, size=512, seed=123):
