@@ -1,0 +1,135 @@
+/*
+ * rgrg_b200 — C ABI of the B200-native region-guided report-generation inference engine.
+ *
+ * Drop-in boundary for the reference's inference path (ttanida/rgrg @ 9520b6d):
+ *   ReportGenerationModel.generate()            src/full_model/report_generation_model.py:212-276
+ *   LanguageModel.generate()                    src/language_model/language_model.py:401-479
+ *   ObjectDetector.forward() (inference)        src/object_detector/object_detector.py:184-261
+ * The reference has no FFI of its own (100 % Python); these are the entry points a ctypes / cffi binding on the
+ * reference side would bind (INTEGRATION.md shows that binding).  Plain pointers and sizes only, no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; rgrg_last_error() then describes the failure
+ *     (CUDA allocation failures contain the substring "out of memory", which callers of the reference
+ *     string-match: src/full_model/evaluate_full_model/evaluate_language_model.py:1208);
+ *   - one engine per GPU, not thread-safe, calls serialised by the caller (as in the reference: one Python thread);
+ *   - the engine owns weights (device copies, repacked), workspace and KV cache; callers own inputs and outputs;
+ *   - "dev" pointers are CUDA device pointers on the engine's device, "host" pointers are ordinary host memory;
+ *   - `stream` is a cudaStream_t (NULL = default stream); work is enqueued on it and the call returns after the
+ *     results it hands back on the host are complete.
+ */
+#ifndef RGRG_B200_H
+#define RGRG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rgrg_engine rgrg_engine_t;
+
+#if defined(__GNUC__)
+#define RGRG_API __attribute__((visibility("default")))
+#else
+#define RGRG_API
+#endif
+
+#define RGRG_NUM_REGIONS 29
+#define RGRG_VOCAB 50257
+#define RGRG_EOS 50256
+#define RGRG_MAX_PROPOSALS 1000
+
+/* ---- lifecycle ------------------------------------------------------------------------------------------------ */
+
+/* replaces: ReportGenerationModel.__init__ + .to(device) (generate_reports_for_images.py:160-163) */
+RGRG_API int rgrg_create(int device, rgrg_engine_t** out);
+RGRG_API void rgrg_destroy(rgrg_engine_t* e);
+RGRG_API const char* rgrg_last_error(const rgrg_engine_t* e); /* e may be NULL: error of the last failed rgrg_create */
+RGRG_API const char* rgrg_version(void);
+
+/* replaces: model.load_state_dict(checkpoint["model"]) (generate_reports_for_images.py:161).
+ * `name` is the reference's state_dict key; fp32 host data, borrowed until rgrg_finalize_weights() returns.
+ * Unknown / unused keys (wpe, causal_mask, alias trees ...) are accepted and ignored. */
+RGRG_API int rgrg_load_weight(rgrg_engine_t* e, const char* name, const float* host_data, const int64_t* shape, int ndim);
+/* folds BatchNorm, repacks to K-major bf16, uploads.  Fails listing the first missing key. */
+RGRG_API int rgrg_finalize_weights(rgrg_engine_t* e);
+
+/* ---- the hot path ---------------------------------------------------------------------------------------------- */
+
+/* replaces: ReportGenerationModel.generate(images, max_length, num_beams=1) (report_generation_model.py:212-276).
+ * images: fp32 [B,1,S,S] (host or device).  Host outputs:
+ *   out_ids      int32 [B*29, max_length]  rows 0..R-1 valid (image-major, region-minor order of selected regions),
+ *                                          column 0 = BOS, finished rows padded with 50256
+ *   out_width    reference width of the id matrix (greedy_search returns [R, out_width], language_model.py:652)
+ *   out_selected uint8 [B,29]; out_detected uint8 [B,29]; out_boxes fp32 [B,29,4]; out_scores fp32 [B,29]
+ *   out_R        number of selected regions (0 -> the reference returns -1, report_generation_model.py:260-261) */
+RGRG_API int rgrg_generate(rgrg_engine_t* e, const float* images, int images_on_host, int B, int S, int max_length,
+                  int num_beams, int early_stopping, int32_t* out_ids, int* out_width, uint8_t* out_selected,
+                  uint8_t* out_detected, float* out_boxes, float* out_scores, int* out_R, void* stream);
+
+/* replaces: LanguageModel.generate(image_hidden_states[R,1024], max_length) (language_model.py:401-479; the entry the
+ * bbox-variation caller uses directly, evaluate_bbox_variations.py:131-136).  feats fp32 [R,1024] host or device. */
+RGRG_API int rgrg_lm_generate(rgrg_engine_t* e, const float* feats, int feats_on_host, int R, int max_length, int num_beams,
+                     int early_stopping, int32_t* out_ids /* host [R, max_length] */, int* out_width, void* stream);
+
+/* replaces: ObjectDetector.forward(images) + BinaryClassifierRegionSelection.forward (inference branch).
+ * Host outputs as in rgrg_generate; out_region_features fp32 host [B,29,1024] (may be NULL);
+ * out_top_idx int32 host [B,29] (may be NULL), out_num_proposals int32 host [B] (may be NULL). */
+RGRG_API int rgrg_detect(rgrg_engine_t* e, const float* images, int images_on_host, int B, int S, uint8_t* out_selected,
+                uint8_t* out_detected, float* out_boxes, float* out_scores, float* out_region_features,
+                int32_t* out_top_idx, int32_t* out_num_proposals, int* out_R, void* stream);
+
+/* ---- stage-level entry points (teacher-forced parity tests and the roofline harness call these) ---------------- */
+
+/* decoder logits with forced tokens: forced_ids int32 dev [R, n_tokens]; out_logits fp32 dev [n_tokens, R, 50257]
+ * (logits after consuming token t, language_model.py:258-399 with the cache of :169-170). */
+RGRG_API int rgrg_lm_forced_logits(rgrg_engine_t* e, const float* feats_dev, int R, const int32_t* forced_ids_dev,
+                          int n_tokens, float* out_logits_dev, void* stream);
+
+/* RPN filter_proposals (torchvision rpn.py:242-297) on given fp32 head outputs.
+ * objectness dev [B,N]; deltas dev [B,N,4] (or NULL when decoded_boxes dev [B,N,4] is given); N = feat*feat*160.
+ * outputs (dev): boxes [B,1000,4], scores [B,1000], count [B], topk_idx [B,1000] (opt), keep_rank [B,1000] (opt) */
+RGRG_API int rgrg_rpn_filter(rgrg_engine_t* e, const float* objectness_dev, const float* deltas_dev, const float* decoded_dev,
+                    int B, int feat, int image_size, float* boxes_dev, float* scores_dev, int32_t* count_dev,
+                    int32_t* topk_idx_dev, int32_t* keep_rank_dev, void* stream);
+
+/* RoIAlign 8x8 / sampling 2 (torchvision roi_align.py) : feats bf16 NHWC dev [B,f,f,C]; boxes dev [B,1000,4];
+ * count dev [B]; out bf16 dev [sum(count), 64, C] (row order: image-major) */
+RGRG_API int rgrg_roi_align(rgrg_engine_t* e, const void* feats_bf16_dev, const float* boxes_dev, const int32_t* count_dev,
+                   int B, int feat, int C, int image_size, void* out_bf16_dev, void* stream);
+
+/* per-class top-1 selection (custom_roi_heads.py:63-208): class_logits dev [sum(count),30], box_regression dev
+ * [sum(count),120]; outputs dev: detected uint8 [B,29], top_idx int32 [B,29], scores [B,29], boxes [B,29,4] */
+RGRG_API int rgrg_roi_tail(rgrg_engine_t* e, const float* class_logits_dev, const float* box_regression_dev,
+                  const float* boxes_dev, const int32_t* count_dev, int B, int image_size, uint8_t* detected_dev,
+                  int32_t* top_idx_dev, float* scores_dev, float* top_boxes_dev, void* stream);
+
+/* D[M,N] (fp32 dev) = A[M,K] (bf16 dev) * W[N,K]^T (bf16 dev) + bias[N] (fp32 dev or NULL).
+ * impl: 0 = tcgen05 BN=128, 1 = tcgen05 BN=64, 2 = CUDA-core cross-check.  act: 0 none, 1 relu, 2 gelu_new. */
+RGRG_API int rgrg_gemm_bf16(rgrg_engine_t* e, const void* A_dev, const void* W_dev, const float* bias_dev, int M, int N, int K,
+                   int act, int impl, float* out_dev, void* stream);
+
+/* 3x3 / pad 1 / stride 1 conv, NHWC: in bf16 dev [B,H,W,Cin]; w bf16 dev [Cout, 9*Cin] (tap-major); out fp32 dev
+ * [B,H,W,Cout].  implicit: 1 = TMA implicit GEMM (4-D tensor map, OOB zero fill), 0 = im2col + GEMM. */
+RGRG_API int rgrg_conv3x3_bf16(rgrg_engine_t* e, const void* in_dev, const void* w_dev, const float* bias_dev, int B, int H,
+                      int W, int Cin, int Cout, int relu, int implicit, float* out_dev, void* stream);
+
+/* backbone only: images fp32 dev [B,1,S,S] -> features bf16 NHWC dev [B,S/32,S/32,2048] */
+RGRG_API int rgrg_backbone(rgrg_engine_t* e, const float* images_dev, int B, int S, void* out_feats_bf16_dev, void* stream);
+
+/* copy a named internal buffer of the last call to the host (tests): "rpn_out" fp32 [B*f*f,800],
+ * "features" bf16 [B,f,f,2048], "pred_out" fp32 [P,150], "proposals" fp32 [B,1000,4], "selection_logits" fp32 [B*29] */
+RGRG_API int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst, size_t bytes);
+
+/* behaviour switches: "implicit_conv" (0/1), "cuda_graph" (0/1), "gemm_impl" (0 tcgen05, 2 CUDA-core cross-check) */
+RGRG_API int rgrg_set_option(rgrg_engine_t* e, const char* key, int value);
+
+/* counters since creation: kernels launched by this library (bench.py's gpu_launches claim) */
+RGRG_API int64_t rgrg_kernel_launches(const rgrg_engine_t* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RGRG_B200_H */

@@ -1,0 +1,74 @@
+// Shared helpers for the rgrg_b200 engine (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+typedef __nv_bfloat16 bf16;
+
+namespace rgrg {
+
+struct CudaError : std::runtime_error {
+  cudaError_t code;
+  CudaError(cudaError_t c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+
+inline void cuda_check(cudaError_t e, const char* expr, const char* file, int line) {
+  if (e != cudaSuccess) {
+    std::string msg = std::string("CUDA error: ") + cudaGetErrorString(e) + " (" + expr + ") at " + file + ":" +
+                      std::to_string(line);
+    // callers of the reference string-match "out of memory" (evaluate_language_model.py:1208)
+    if (e == cudaErrorMemoryAllocation && msg.find("out of memory") == std::string::npos) msg += " [out of memory]";
+    cudaGetLastError();
+    throw CudaError(e, msg);
+  }
+}
+#define CUDA_CHECK(x) ::rgrg::cuda_check((x), #x, __FILE__, __LINE__)
+#define KERNEL_CHECK() CUDA_CHECK(cudaGetLastError())
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float bf2f(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ bf16 f2bf(float v) { return __float2bfloat16_rn(v); }
+
+// 8 bf16 <-> 8 floats through one 16-byte vector
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// transformers activations.py NewGELUActivation: 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
+__device__ __forceinline__ float gelu_new(float x) {
+  const float k = 0.7978845608028654f;
+  float inner = k * (x + 0.044715f * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(inner));
+}
+
+}  // namespace rgrg

@@ -1,0 +1,1158 @@
+// rgrg_b200 engine: weights, workspace, orchestration of the generate() path and the C ABI (include/rgrg_b200.h).
+// Reference call stack being replaced: SURVEY.md §3b-§3c (report_generation_model.py:212-276 ->
+// object_detector.py:184-261 -> custom_rpn.py:53-85 / custom_roi_heads.py:210-269 ->
+// binary_classifier_region_selection.py:24-68 -> language_model.py:401-479, :609-652).
+#include <cuda.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <type_traits>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/rgrg_b200.h"
+#include "common.cuh"
+#include "decoder_kernels.cuh"
+#include "detector_kernels.cuh"
+#include "epilogues.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+
+using namespace rgrg;
+
+namespace {
+
+constexpr int NLAYER = 24;
+constexpr int DM = 1024;
+constexpr int VOCAB = 50257;
+constexpr int NREG = 29;
+constexpr int TOPK = det::TOPK;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  void ensure(size_t n) {
+    if (n <= bytes) return;
+    release();
+    CUDA_CHECK(cudaMalloc(&p, n));
+    bytes = n;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostRef {
+  const float* p;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+// K-major bf16 weight [N, K] + fp32 bias, with TMA maps for both N-tile widths
+struct Linear {
+  bf16* w = nullptr;
+  float* bias = nullptr;
+  int N = 0, K = 0;
+  CUtensorMap tm128, tm64;
+  void make_maps() {
+    tm128 = tc::make_tmap_2d(w, N, K, 128);
+    tm64 = tc::make_tmap_2d(w, N, K, 64);
+  }
+};
+struct LinearF32 {
+  float* w = nullptr;
+  float* bias = nullptr;
+  int N = 0, K = 0;
+};
+
+struct BlockW {
+  Linear c1, c2, c3, ds;
+  int cin, width, cout, stride;
+  bool has_ds;
+};
+
+struct LayerW {
+  float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  Linear attn, proj, fc, mproj;
+};
+
+}  // namespace
+
+struct rgrg_engine {
+  int device = 0;
+  std::string err;
+  int64_t launches = 0;
+  bool weights_ready = false;
+  int opt_implicit_conv = 0;
+  int opt_cuda_graph = 1;
+  int opt_gemm_impl = 0;
+  std::unordered_map<std::string, HostRef> host;
+  std::vector<void*> weight_allocs;
+
+  // ---- weights
+  float *stem_w = nullptr, *stem_b = nullptr;
+  std::vector<BlockW> blocks;
+  Linear rpn_conv, rpn_heads, fc6, fc7, pred;
+  LinearF32 dimred, sel0, sel2, sel4;
+  Linear fst0, fst2, ukv, lm_head;
+  float* wte_f32 = nullptr;
+  LayerW layers[NLAYER];
+  float *lnf_g = nullptr, *lnf_b = nullptr;
+
+  // ---- workspace (detector)
+  int ws_B = 0, ws_S = 0;
+  DevBuf images, act[2], t1, t2, idb, sub, col, feats, rpn_t, rpn_out;
+  DevBuf prop_boxes, prop_scores, prop_count, roi_off, pooled, f6, f7, pred_out;
+  DevBuf detected, top_idx, top_scores, top_boxes, mean2048, trf, s0, s1, sel_logits, selected, sel_rows, num_sel;
+  DevBuf lm_in;
+  // ---- workspace (decoder)
+  int ws_rows = 0, ws_slots = 0;
+  DevBuf kv_cache, h, x, q, attn_o, mlp_mid, a1, img, part_val, part_idx, ids, unfinished, unf_count, step, logits_tmp;
+  int last_B = 0, last_S = 0, last_P = 0;
+
+  // ---- CUDA graph of one decode step, keyed by row count
+  std::map<int, cudaGraphExec_t> step_graphs;
+  std::map<int, int> step_graph_nodes;
+
+  ~rgrg_engine() {
+    for (auto& g : step_graphs) cudaGraphExecDestroy(g.second);
+    for (void* p : weight_allocs) cudaFree(p);
+    DevBuf* all[] = {&images, &act[0], &act[1], &t1, &t2, &idb, &sub, &col, &feats, &rpn_t, &rpn_out, &prop_boxes,
+                     &prop_scores, &prop_count, &roi_off, &pooled, &f6, &f7, &pred_out, &detected, &top_idx,
+                     &top_scores, &top_boxes, &mean2048, &trf, &s0, &s1, &sel_logits, &selected, &sel_rows, &num_sel,
+                     &lm_in, &kv_cache, &h, &x, &q, &attn_o, &mlp_mid, &a1, &img, &part_val, &part_idx, &ids,
+                     &unfinished, &unf_count, &step, &logits_tmp};
+    for (DevBuf* b : all) b->release();
+  }
+
+  template <class T>
+  T* walloc(size_t n) {
+    void* p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, n * sizeof(T)));
+    weight_allocs.push_back(p);
+    return reinterpret_cast<T*>(p);
+  }
+
+  // ================================================================================================================
+  // GEMM dispatch
+  // ================================================================================================================
+  template <class Epi>
+  void gemm(const bf16* A, int M, const Linear& W, const Epi& epi, cudaStream_t st, bool m_fastest, int force_bn = 0) {
+    if (M <= 0) return;
+    if (opt_gemm_impl == 2) {
+      if constexpr (std::is_same<Epi, EpiArgmaxPartial>::value) {
+        throw std::runtime_error("arg-max epilogue has no CUDA-core variant");
+      } else {
+        simt::launch<bf16, bf16, Epi>(A, W.w, M, W.N, W.K, epi, st);
+        ++launches;
+        return;
+      }
+    }
+    if (W.K % 64 != 0) throw std::runtime_error("GEMM K must be a multiple of 64");
+    const int mt = ceil_div(M, tc::BM);
+    int bn = force_bn;
+    if (!bn) {
+      bn = 128;
+      if (W.N <= 64) bn = 64;
+      else if (mt * ceil_div(W.N, 128) < 148) bn = 64;  // under one wave: halve the tile to occupy more SMs
+    }
+    tc::GemmShape s{};
+    s.M = M;
+    s.N = W.N;
+    s.k_iters = W.K / 64;
+    s.m_tiles = mt;
+    s.n_tiles = ceil_div(W.N, bn);
+    s.m_fastest = m_fastest ? 1 : 0;
+    CUtensorMap tmA = tc::make_tmap_2d(A, M, W.K, 128);
+    if (bn == 128) tc::launch<128, 6, Epi>(tmA, W.tm128, s, epi, st);
+    else tc::launch<64, 4, Epi>(tmA, W.tm64, s, epi, st);
+    ++launches;
+  }
+
+  // 3x3 / stride 1 / pad 1 conv as implicit GEMM through a 4-D tensor map (K loop = 9 taps x Cin/64)
+  template <class Epi>
+  void conv3x3_implicit(const bf16* in, int B, int H, int Wd, int Cin, const Linear& W, const Epi& epi, cudaStream_t st) {
+    if (H % 8 || Wd % 16 || Cin % 64) throw std::runtime_error("implicit conv needs H%8==0, W%16==0, Cin%64==0");
+    tc::GemmShape s{};
+    s.M = B * H * Wd;
+    s.N = W.N;
+    s.conv = 1;
+    s.kc_blocks = Cin / 64;
+    s.k_iters = 9 * s.kc_blocks;
+    s.H = H;
+    s.W = Wd;
+    s.tiles_w = Wd / 16;
+    s.tiles_h = H / 8;
+    s.m_tiles = B * s.tiles_w * s.tiles_h;
+    const int bn = (W.N <= 64) ? 64 : 128;
+    s.n_tiles = ceil_div(W.N, bn);
+    s.m_fastest = 0;
+    CUtensorMap tmA = tc::make_tmap_nhwc(in, B, H, Wd, Cin);
+    if (bn == 128) tc::launch<128, 6, Epi>(tmA, W.tm128, s, epi, st);
+    else tc::launch<64, 4, Epi>(tmA, W.tm64, s, epi, st);
+    ++launches;
+  }
+
+  void im2col(const bf16* in, bf16* colbuf, int B, int H, int Wd, int C, int stride, cudaStream_t st) {
+    const int Ho = H / stride, Wo = Wd / stride;
+    const size_t total = static_cast<size_t>(B) * Ho * Wo * 9 * (C / 8);
+    const int grid = static_cast<int>(std::min<size_t>(ceil_div64(total, 256), 148 * 16));
+    det::im2col3x3_kernel<<<grid, 256, 0, st>>>(in, colbuf, B, H, Wd, C, stride, Ho, Wo);
+    KERNEL_CHECK();
+    ++launches;
+  }
+
+  template <class Epi>
+  void conv3x3(const bf16* in, int B, int H, int Wd, int Cin, int stride, const Linear& W, const Epi& epi, cudaStream_t st) {
+    if (stride == 1 && opt_implicit_conv && opt_gemm_impl != 2) {
+      conv3x3_implicit(in, B, H, Wd, Cin, W, epi, st);
+    } else {
+      const int Ho = H / stride, Wo = Wd / stride;
+      col.ensure(static_cast<size_t>(B) * Ho * Wo * 9 * Cin * 2);
+      im2col(in, col.as<bf16>(), B, H, Wd, Cin, stride, st);
+      gemm(col.as<bf16>(), B * Ho * Wo, W, epi, st, false);
+    }
+  }
+
+  static EpiStore store_bf16(bf16* out, const float* bias, int ldc, int act, const bf16* res = nullptr) {
+    EpiStore e{};
+    e.out_bf16 = out;
+    e.bias = bias;
+    e.ldc = ldc;
+    e.act = act;
+    e.res_bf16 = res;
+    return e;
+  }
+  static EpiStore store_f32(float* out, const float* bias, int ldc, int act, const float* res = nullptr) {
+    EpiStore e{};
+    e.out_f32 = out;
+    e.bias = bias;
+    e.ldc = ldc;
+    e.act = act;
+    e.res_f32 = res;
+    return e;
+  }
+
+  // ================================================================================================================
+  // weights
+  // ================================================================================================================
+  const HostRef& need(const std::string& name) {
+    auto it = host.find(name);
+    if (it == host.end()) throw std::runtime_error("missing weight: " + name);
+    return it->second;
+  }
+  const HostRef& need_any(const std::string& a, const std::string& b) {
+    auto it = host.find(a);
+    if (it != host.end()) return it->second;
+    return need(b);
+  }
+
+  DevBuf stage, stage2;
+  const float* upload(const HostRef& r, DevBuf& buf) {
+    buf.ensure(static_cast<size_t>(r.numel()) * 4);
+    CUDA_CHECK(cudaMemcpy(buf.p, r.p, static_cast<size_t>(r.numel()) * 4, cudaMemcpyHostToDevice));
+    return buf.as<float>();
+  }
+  float* upload_keep(const HostRef& r) {
+    float* d = walloc<float>(r.numel());
+    CUDA_CHECK(cudaMemcpy(d, r.p, static_cast<size_t>(r.numel()) * 4, cudaMemcpyHostToDevice));
+    return d;
+  }
+  static int grid_for(long long n) { return static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 32)); }
+
+  // conv weight [Cout, Cin, k, k] (+ optional BN fold) -> bf16 [Cout, k*k*Cin]; returns Linear with bias
+  Linear make_conv(const std::string& conv, const std::string& bn, bool has_conv_bias) {
+    const HostRef& w = need(conv + ".weight");
+    const int cout = static_cast<int>(w.shape[0]), cin = static_cast<int>(w.shape[1]);
+    const int R = static_cast<int>(w.shape[2] * w.shape[3]);
+    Linear L;
+    L.N = cout;
+    L.K = cin * R;
+    L.w = walloc<bf16>(static_cast<size_t>(L.N) * L.K);
+    L.bias = walloc<float>(cout);
+    const float* dw = upload(w, stage);
+    float* scale = nullptr;
+    if (!bn.empty()) {
+      float* g = upload_tmp(need(bn + ".weight"));
+      float* b = upload_tmp(need(bn + ".bias"));
+      float* m = upload_tmp(need(bn + ".running_mean"));
+      float* v = upload_tmp(need(bn + ".running_var"));
+      scale = tmp_alloc(cout);
+      det::bn_fold_kernel<<<ceil_div(cout, 256), 256>>>(g, b, m, v, scale, L.bias, cout, 1e-5f);
+      KERNEL_CHECK();
+    } else if (has_conv_bias) {
+      CUDA_CHECK(cudaMemcpy(L.bias, need(conv + ".bias").p, cout * 4, cudaMemcpyHostToDevice));
+    } else {
+      CUDA_CHECK(cudaMemset(L.bias, 0, cout * 4));
+    }
+    det::repack_oihw_kernel<bf16><<<grid_for(static_cast<long long>(L.N) * L.K), 256>>>(dw, L.w, scale, L.N, cin, R);
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaDeviceSynchronize());
+    free_tmps();
+    L.make_maps();
+    return L;
+  }
+  std::vector<void*> tmps;
+  float* tmp_alloc(size_t n) {
+    void* p;
+    CUDA_CHECK(cudaMalloc(&p, n * 4));
+    tmps.push_back(p);
+    return reinterpret_cast<float*>(p);
+  }
+  float* upload_tmp(const HostRef& r) {
+    float* d = tmp_alloc(r.numel());
+    CUDA_CHECK(cudaMemcpy(d, r.p, static_cast<size_t>(r.numel()) * 4, cudaMemcpyHostToDevice));
+    return d;
+  }
+  void free_tmps() {
+    for (void* p : tmps) cudaFree(p);
+    tmps.clear();
+  }
+
+  // nn.Linear weight [N, K] (already K-major) -> bf16 rows [row0, row0+N) of dst
+  void put_linear_rows(const std::string& name, bf16* dst_w, float* dst_b, int row0, int K) {
+    const HostRef& w = need(name + ".weight");
+    const int N = static_cast<int>(w.shape[0]);
+    if (w.numel() != static_cast<int64_t>(N) * K) throw std::runtime_error("bad shape for " + name);
+    const float* dw = upload(w, stage);
+    det::cast_bf16_kernel<<<grid_for(w.numel()), 256>>>(dw, dst_w + static_cast<size_t>(row0) * K, w.numel());
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaMemcpy(dst_b + row0, need(name + ".bias").p, N * 4, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaDeviceSynchronize());
+  }
+  Linear make_linear(const std::string& name) {
+    const HostRef& w = need(name + ".weight");
+    Linear L;
+    L.N = static_cast<int>(w.shape[0]);
+    L.K = static_cast<int>(w.numel() / w.shape[0]);
+    L.w = walloc<bf16>(static_cast<size_t>(L.N) * L.K);
+    L.bias = walloc<float>(L.N);
+    put_linear_rows(name, L.w, L.bias, 0, L.K);
+    L.make_maps();
+    return L;
+  }
+  // HF Conv1D weight [K, N] -> K-major bf16 [N, K]
+  Linear make_conv1d(const std::string& name) {
+    const HostRef& w = need(name + ".weight");
+    Linear L;
+    L.K = static_cast<int>(w.shape[0]);
+    L.N = static_cast<int>(w.shape[1]);
+    L.w = walloc<bf16>(static_cast<size_t>(L.N) * L.K);
+    L.bias = upload_keep(need(name + ".bias"));
+    const float* dw = upload(w, stage);
+    dim3 grid(ceil_div(L.N, 32), ceil_div(L.K, 32)), block(32, 8);
+    det::repack_transpose_kernel<<<grid, block>>>(dw, L.w, L.K, L.N);
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaDeviceSynchronize());
+    L.make_maps();
+    return L;
+  }
+  LinearF32 make_linear_f32(const std::string& name) {
+    const HostRef& w = need(name + ".weight");
+    LinearF32 L;
+    L.N = static_cast<int>(w.shape[0]);
+    L.K = static_cast<int>(w.numel() / w.shape[0]);
+    L.w = upload_keep(w);
+    L.bias = upload_keep(need(name + ".bias"));
+    return L;
+  }
+
+  void finalize() {
+    CUDA_CHECK(cudaSetDevice(device));
+    const std::string bb = "object_detector.backbone";
+    // ---- stem (object_detector.py:54: conv1 replaced by a 1-channel 7x7)
+    {
+      const HostRef& w = need(bb + ".0.weight");
+      if (w.numel() != 64 * 49) throw std::runtime_error("conv1 must be [64,1,7,7]");
+      float* dw = upload_tmp(w);
+      float* g = upload_tmp(need(bb + ".1.weight"));
+      float* b = upload_tmp(need(bb + ".1.bias"));
+      float* m = upload_tmp(need(bb + ".1.running_mean"));
+      float* v = upload_tmp(need(bb + ".1.running_var"));
+      float* scale = tmp_alloc(64);
+      stem_w = walloc<float>(49 * 64);
+      stem_b = walloc<float>(64);
+      det::bn_fold_kernel<<<1, 64>>>(g, b, m, v, scale, stem_b, 64, 1e-5f);
+      det::repack_stem_kernel<<<ceil_div(49 * 64, 256), 256>>>(dw, scale, stem_w);
+      KERNEL_CHECK();
+      CUDA_CHECK(cudaDeviceSynchronize());
+      free_tmps();
+    }
+    // ---- 16 bottlenecks (torchvision resnet.py Bottleneck, v1.5: stride on conv2)
+    blocks.clear();
+    const int nblk[4] = {3, 4, 6, 3}, widths[4] = {64, 128, 256, 512};
+    int cin = 64;
+    for (int li = 0; li < 4; ++li) {
+      for (int bi = 0; bi < nblk[li]; ++bi) {
+        const std::string p = bb + "." + std::to_string(4 + li) + "." + std::to_string(bi);
+        BlockW bw;
+        bw.cin = cin;
+        bw.width = widths[li];
+        bw.cout = widths[li] * 4;
+        bw.stride = (bi == 0 && li > 0) ? 2 : 1;
+        bw.has_ds = bi == 0;
+        bw.c1 = make_conv(p + ".conv1", p + ".bn1", false);
+        bw.c2 = make_conv(p + ".conv2", p + ".bn2", false);
+        bw.c3 = make_conv(p + ".conv3", p + ".bn3", false);
+        if (bw.has_ds) bw.ds = make_conv(p + ".downsample.0", p + ".downsample.1", false);
+        blocks.push_back(bw);
+        cin = bw.cout;
+      }
+    }
+    // ---- RPN head (torchvision rpn.py RPNHead); old checkpoints name the conv "conv" instead of "conv.0.0"
+    const std::string rp = "object_detector.rpn.head";
+    if (host.count(rp + ".conv.0.0.weight")) rpn_conv = make_conv(rp + ".conv.0.0", "", true);
+    else rpn_conv = make_conv(rp + ".conv", "", true);
+    {
+      rpn_heads.N = 800;
+      rpn_heads.K = 2048;
+      rpn_heads.w = walloc<bf16>(800 * 2048);
+      rpn_heads.bias = walloc<float>(800);
+      put_linear_rows(rp + ".cls_logits", rpn_heads.w, rpn_heads.bias, 0, 2048);
+      put_linear_rows(rp + ".bbox_pred", rpn_heads.w, rpn_heads.bias, 160, 2048);
+      rpn_heads.make_maps();
+    }
+    // ---- RoI heads: fc6 input is flattened (c, ph, pw) in the reference; our RoIAlign emits (bin, c)
+    const std::string rh = "object_detector.roi_heads";
+    {
+      const HostRef& w = need(rh + ".box_head.fc6.weight");
+      fc6.N = 1024;
+      fc6.K = 2048 * 64;
+      if (w.numel() != static_cast<int64_t>(fc6.N) * fc6.K) throw std::runtime_error("fc6 must be [1024, 131072]");
+      fc6.w = walloc<bf16>(static_cast<size_t>(fc6.N) * fc6.K);
+      fc6.bias = upload_keep(need(rh + ".box_head.fc6.bias"));
+      const float* dw = upload(w, stage);
+      det::repack_oihw_kernel<bf16><<<grid_for(w.numel()), 256>>>(dw, fc6.w, nullptr, fc6.N, 2048, 64);
+      KERNEL_CHECK();
+      CUDA_CHECK(cudaDeviceSynchronize());
+      fc6.make_maps();
+    }
+    fc7 = make_linear(rh + ".box_head.fc7");
+    {
+      pred.N = 150;
+      pred.K = 1024;
+      pred.w = walloc<bf16>(150 * 1024);
+      pred.bias = walloc<float>(150);
+      put_linear_rows(rh + ".box_predictor.cls_score", pred.w, pred.bias, 0, 1024);
+      put_linear_rows(rh + ".box_predictor.bbox_pred", pred.w, pred.bias, 30, 1024);
+      pred.make_maps();
+    }
+    dimred = make_linear_f32(rh + ".dim_reduction");
+    sel0 = make_linear_f32("binary_classifier_region_selection.classifier.0");
+    sel2 = make_linear_f32("binary_classifier_region_selection.classifier.2");
+    sel4 = make_linear_f32("binary_classifier_region_selection.classifier.4");
+    // ---- language model (canonical alias set: language_model.gpt2_blocks.* etc.)
+    const std::string lm = "language_model";
+    fst0 = make_linear(lm + ".feature_space_transformation_nn.0");
+    fst2 = make_linear(lm + ".feature_space_transformation_nn.2");
+    ukv.N = NLAYER * 2 * DM;
+    ukv.K = DM;
+    ukv.w = walloc<bf16>(static_cast<size_t>(ukv.N) * DM);
+    ukv.bias = walloc<float>(ukv.N);
+    for (int l = 0; l < NLAYER; ++l) {
+      const std::string p = lm + ".gpt2_blocks." + std::to_string(l);
+      LayerW& L = layers[l];
+      L.ln1_g = upload_keep(need(p + ".0.weight"));
+      L.ln1_b = upload_keep(need(p + ".0.bias"));
+      L.ln2_g = upload_keep(need(p + ".2.weight"));
+      L.ln2_b = upload_keep(need(p + ".2.bias"));
+      L.attn = make_conv1d(p + ".1.c_attn");
+      L.proj = make_conv1d(p + ".1.c_proj");
+      L.fc = make_conv1d(p + ".3.c_fc");
+      L.mproj = make_conv1d(p + ".3.c_proj");
+      put_linear_rows(p + ".1.uk", ukv.w, ukv.bias, l * 2048, DM);
+      put_linear_rows(p + ".1.uv", ukv.w, ukv.bias, l * 2048 + 1024, DM);
+    }
+    ukv.make_maps();
+    lnf_g = upload_keep(need(lm + ".final_layernorm.weight"));
+    lnf_b = upload_keep(need(lm + ".final_layernorm.bias"));
+    {
+      const HostRef& w = need_any(lm + ".wte.weight", lm + ".lm_head.weight");
+      if (w.numel() != static_cast<int64_t>(VOCAB) * DM) throw std::runtime_error("wte must be [50257,1024]");
+      wte_f32 = upload_keep(w);
+      lm_head.N = VOCAB;
+      lm_head.K = DM;
+      lm_head.w = walloc<bf16>(static_cast<size_t>(VOCAB) * DM);
+      lm_head.bias = nullptr;
+      det::cast_bf16_kernel<<<grid_for(w.numel()), 256>>>(wte_f32, lm_head.w, w.numel());
+      KERNEL_CHECK();
+      lm_head.make_maps();
+    }
+    // ---- base anchors (torchvision anchor_utils.py generate_anchors: ratio-major, size-minor, round half-even)
+    {
+      const float sizes[10] = {20, 40, 60, 80, 100, 120, 140, 160, 180, 300};
+      const float ratios[16] = {0.2f, 0.25f, 0.4f, 0.5f, 0.6f, 0.7f, 0.8f, 0.9f, 1.0f, 1.3f, 1.5f, 2.1f, 2.6f, 3.0f, 5.0f, 8.0f};
+      float base[160 * 4];
+      for (int r = 0; r < 16; ++r) {
+        const float hr = sqrtf(ratios[r]);
+        const float wr = 1.0f / hr;
+        for (int s = 0; s < 10; ++s) {
+          const float ws = wr * sizes[s], hs = hr * sizes[s];
+          float* a = base + (r * 10 + s) * 4;
+          a[0] = nearbyintf(-ws / 2.0f);
+          a[1] = nearbyintf(-hs / 2.0f);
+          a[2] = nearbyintf(ws / 2.0f);
+          a[3] = nearbyintf(hs / 2.0f);
+        }
+      }
+      CUDA_CHECK(cudaMemcpyToSymbol(det::c_base_anchors, base, sizeof(base)));
+    }
+    CUDA_CHECK(cudaDeviceSynchronize());
+    stage.release();
+    stage2.release();
+    host.clear();
+    CUDA_CHECK(cudaFuncSetAttribute(det::rpn_proposals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(det::RPN_SMEM)));
+    weights_ready = true;
+  }
+
+  // ================================================================================================================
+  // detector
+  // ================================================================================================================
+  void ensure_detector_ws(int B, int S) {
+    if (B <= ws_B && S <= ws_S) return;
+    B = std::max(B, ws_B);
+    S = std::max(S, ws_S);
+    const size_t P = S / 4, f = S / 32;
+    images.ensure(static_cast<size_t>(B) * S * S * 4);
+    const size_t big = static_cast<size_t>(B) * P * P * 256 * 2;  // layer1 output is the largest activation
+    act[0].ensure(big);
+    act[1].ensure(big);
+    t1.ensure(static_cast<size_t>(B) * P * P * 128 * 2);  // layer2.0.conv1 runs at full layer-1 resolution
+    t2.ensure(static_cast<size_t>(B) * P * P * 64 * 2);
+    idb.ensure(big);
+    sub.ensure(big / 4);
+    feats.ensure(static_cast<size_t>(B) * f * f * 2048 * 2);
+    rpn_t.ensure(static_cast<size_t>(B) * f * f * 2048 * 2);
+    rpn_out.ensure(static_cast<size_t>(B) * f * f * 800 * 4);
+    prop_boxes.ensure(static_cast<size_t>(B) * TOPK * 4 * 4);
+    prop_scores.ensure(static_cast<size_t>(B) * TOPK * 4);
+    prop_count.ensure(static_cast<size_t>(B) * 4);
+    roi_off.ensure(static_cast<size_t>(B + 1) * 4);
+    const size_t rows = static_cast<size_t>(B) * NREG;
+    detected.ensure(rows);
+    top_idx.ensure(rows * 4);
+    top_scores.ensure(rows * 4);
+    top_boxes.ensure(rows * 16);
+    mean2048.ensure(rows * 2048 * 4);
+    trf.ensure(rows * 1024 * 4);
+    s0.ensure(rows * 512 * 4);
+    s1.ensure(rows * 128 * 4);
+    sel_logits.ensure(rows * 4);
+    selected.ensure(rows);
+    sel_rows.ensure(rows * 4);
+    num_sel.ensure(4);
+    lm_in.ensure(rows * 1024 * 2);
+    ws_B = B;
+    ws_S = S;
+  }
+  void ensure_roi_ws(int P_total) {
+    const size_t rows = static_cast<size_t>(std::max(P_total, 1));
+    pooled.ensure(rows * 131072 * 2);
+    f6.ensure(rows * 1024 * 2);
+    f7.ensure(rows * 1024 * 2);
+    pred_out.ensure(rows * 150 * 4);
+  }
+
+  // images (device fp32 [B,1,S,S]) -> feats bf16 NHWC
+  void run_backbone(const float* img_dev, int B, int S, bf16* out_feats, cudaStream_t st) {
+    if (S % 128 != 0) throw std::runtime_error("image size must be a multiple of 128");
+    const int P = S / 4;
+    det::stem_kernel<<<dim3(P / 8, P / 8, B), 256, 0, st>>>(img_dev, stem_w, stem_b, act[0].as<bf16>(), S);
+    KERNEL_CHECK();
+    ++launches;
+    int cur = 0, H = P;
+    for (size_t i = 0; i < blocks.size(); ++i) {
+      const BlockW& bw = blocks[i];
+      const bf16* xin = act[cur].as<bf16>();
+      const bool last = (i + 1 == blocks.size());
+      bf16* yout = last ? out_feats : act[cur ^ 1].as<bf16>();
+      const int Ho = H / bw.stride;
+      const int M_in = B * H * H, M_out = B * Ho * Ho;
+      // conv1 1x1 + BN + ReLU
+      gemm(xin, M_in, bw.c1, store_bf16(t1.as<bf16>(), bw.c1.bias, bw.width, ACT_RELU), st, false);
+      // conv2 3x3 (stride here, v1.5) + BN + ReLU
+      conv3x3(t1.as<bf16>(), B, H, H, bw.width, bw.stride, bw.c2, store_bf16(t2.as<bf16>(), bw.c2.bias, bw.width, ACT_RELU), st);
+      // identity / downsample branch
+      const bf16* identity = xin;
+      if (bw.has_ds) {
+        const bf16* ds_in = xin;
+        if (bw.stride == 2) {
+          const size_t total = static_cast<size_t>(M_out) * (bw.cin / 8);
+          det::subsample2_kernel<<<static_cast<int>(std::min<size_t>(ceil_div64(total, 256), 148 * 16)), 256, 0, st>>>(
+              xin, sub.as<bf16>(), B, H, H, bw.cin);
+          KERNEL_CHECK();
+          ++launches;
+          ds_in = sub.as<bf16>();
+        }
+        gemm(ds_in, M_out, bw.ds, store_bf16(idb.as<bf16>(), bw.ds.bias, bw.cout, ACT_NONE), st, false);
+        identity = idb.as<bf16>();
+      }
+      // conv3 1x1 + BN, + identity, ReLU
+      gemm(t2.as<bf16>(), M_out, bw.c3, store_bf16(yout, bw.c3.bias, bw.cout, ACT_RELU, identity), st, false);
+      cur ^= 1;
+      H = Ho;
+    }
+  }
+
+  void run_rpn_filter(const det::RpnIn& in, const det::RpnOut& out, int B, int feat, int S, cudaStream_t st) {
+    det::rpn_proposals_kernel<<<B, det::RPN_THREADS, det::RPN_SMEM, st>>>(in, out, feat * feat * det::NUM_ANCHORS, feat, S, 0.7f);
+    KERNEL_CHECK();
+    ++launches;
+  }
+
+  // full detector + selection; leaves lm_in [R,1024] bf16 on the device; returns R
+  int run_detect(const float* img_dev, int B, int S, cudaStream_t st) {
+    ensure_detector_ws(B, S);
+    const int f = S / 32;
+    run_backbone(img_dev, B, S, feats.as<bf16>(), st);
+    // RPN head: 3x3 conv + ReLU, then both 1x1 heads as one N = 160 + 640 GEMM with fp32 (decision-critical) output
+    conv3x3(feats.as<bf16>(), B, f, f, 2048, 1, rpn_conv, store_bf16(rpn_t.as<bf16>(), rpn_conv.bias, 2048, ACT_RELU), st);
+    gemm(rpn_t.as<bf16>(), B * f * f, rpn_heads, store_f32(rpn_out.as<float>(), rpn_heads.bias, 800, ACT_NONE), st, false);
+    det::RpnIn in{};
+    in.obj = rpn_out.as<float>();
+    in.deltas = rpn_out.as<float>() + 160;
+    in.obj_bs = in.del_bs = static_cast<long long>(f) * f * 800;
+    in.obj_ps = in.del_ps = 800;
+    det::RpnOut out{};
+    out.boxes = prop_boxes.as<float>();
+    out.scores = prop_scores.as<float>();
+    out.count = prop_count.as<int>();
+    run_rpn_filter(in, out, B, f, S, st);
+    det::roi_offsets_kernel<<<1, 32, 0, st>>>(prop_count.as<int>(), roi_off.as<int>(), B);
+    KERNEL_CHECK();
+    ++launches;
+    int P_total = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&P_total, roi_off.as<int>() + B, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));  // the RoI GEMMs are sized by the number of surviving proposals
+    last_P = P_total;
+    ensure_roi_ws(P_total);
+    const float scale = exp2f(roundf(log2f(static_cast<float>(f) / static_cast<float>(S))));  // poolers.py _infer_scale
+    if (P_total > 0) {
+      det::roi_align_kernel<<<dim3(TOPK, B), 256, 0, st>>>(feats.as<bf16>(), prop_boxes.as<float>(), prop_count.as<int>(),
+                                                          roi_off.as<int>(), pooled.as<bf16>(), f, 2048, scale);
+      KERNEL_CHECK();
+      ++launches;
+      gemm(pooled.as<bf16>(), P_total, fc6, store_bf16(f6.as<bf16>(), fc6.bias, 1024, ACT_RELU), st, false);
+      gemm(f6.as<bf16>(), P_total, fc7, store_bf16(f7.as<bf16>(), fc7.bias, 1024, ACT_RELU), st, true);
+      gemm(f7.as<bf16>(), P_total, pred, store_f32(pred_out.as<float>(), pred.bias, 150, ACT_NONE), st, true);
+    }
+    det::RoiTailOut to{detected.as<uint8_t>(), top_idx.as<int>(), top_scores.as<float>(), top_boxes.as<float>()};
+    det::roi_tail_kernel<<<B, 256, 0, st>>>(pred_out.as<float>(), 150, pred_out.as<float>() + 30, 150, prop_boxes.as<float>(),
+                                            prop_count.as<int>(), roi_off.as<int>(), to, S);
+    KERNEL_CHECK();
+    det::roi_mean_kernel<<<dim3(NREG, B), 256, 0, st>>>(feats.as<bf16>(), prop_boxes.as<float>(), prop_count.as<int>(),
+                                                        top_idx.as<int>(), mean2048.as<float>(), f, 2048, scale);
+    KERNEL_CHECK();
+    launches += 2;
+    const int rows = B * NREG;
+    // dim_reduction + selection MLP in fp32 on CUDA cores (decision-critical, 0.01 % of the FLOPs)
+    simt::launch<float, float, EpiStore>(mean2048.as<float>(), dimred.w, rows, 1024, 2048,
+                                         store_f32(trf.as<float>(), dimred.bias, 1024, ACT_NONE), st);
+    simt::launch<float, float, EpiStore>(trf.as<float>(), sel0.w, rows, 512, 1024, store_f32(s0.as<float>(), sel0.bias, 512, ACT_RELU), st);
+    simt::launch<float, float, EpiStore>(s0.as<float>(), sel2.w, rows, 128, 512, store_f32(s1.as<float>(), sel2.bias, 128, ACT_RELU), st);
+    det::selection_tail_kernel<<<1, 1024, 0, st>>>(s1.as<float>(), sel4.w, sel4.bias, detected.as<uint8_t>(), sel_logits.as<float>(),
+                                                   selected.as<uint8_t>(), sel_rows.as<int>(), num_sel.as<int>(), rows);
+    KERNEL_CHECK();
+    det::gather_rows_bf16_kernel<<<rows, 256, 0, st>>>(trf.as<float>(), sel_rows.as<int>(), num_sel.as<int>(), lm_in.as<bf16>(), 1024);
+    KERNEL_CHECK();
+    launches += 5;
+    int R = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&R, num_sel.as<int>(), 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));  // report_generation_model.py:260: R == 0 -> return -1
+    last_B = B;
+    last_S = S;
+    return R;
+  }
+
+  // ================================================================================================================
+  // decoder
+  // ================================================================================================================
+  void ensure_decoder_ws(int rows, int max_length) {
+    const int slots = max_length + 1;
+    if (rows > ws_rows || slots > ws_slots) {
+      const int r = std::max(rows, ws_rows), s = std::max(slots, ws_slots);
+      kv_cache.ensure(static_cast<size_t>(NLAYER) * 2 * r * 16 * s * 64 * 2);
+      const size_t rr = static_cast<size_t>(r);
+      h.ensure(rr * DM * 4);
+      x.ensure(rr * DM * 2);
+      q.ensure(rr * DM * 2);
+      attn_o.ensure(rr * DM * 2);
+      mlp_mid.ensure(rr * 4 * DM * 2);
+      a1.ensure(rr * DM * 2);
+      img.ensure(rr * DM * 2);
+      part_val.ensure(rr * 1024 * 4);
+      part_idx.ensure(rr * 1024 * 4);
+      ids.ensure(rr * (s + 1) * 4);
+      unfinished.ensure(rr * 4);
+      unf_count.ensure(static_cast<size_t>(s + 1) * 4);
+      step.ensure(4);
+      ws_rows = r;
+      ws_slots = s;
+      for (auto& g : step_graphs) cudaGraphExecDestroy(g.second);  // buffers moved: captured pointers are stale
+      step_graphs.clear();
+      step_graph_nodes.clear();
+    }
+  }
+  KvGeom kv_geom() const { return KvGeom{kv_cache.as<bf16>(), ws_rows, ws_slots}; }
+
+  // language_model.py:284 (once instead of every step) + :140-147 for all 24 layers in one GEMM
+  void lm_prologue(const bf16* feats_bf16, int R, int beams, cudaStream_t st) {
+    gemm(feats_bf16, R, fst0, store_bf16(a1.as<bf16>(), fst0.bias, DM, ACT_RELU), st, true);
+    gemm(a1.as<bf16>(), R, fst2, store_bf16(img.as<bf16>(), fst2.bias, DM, ACT_NONE), st, true);
+    EpiImageKv e{ukv.bias, kv_geom(), beams};
+    gemm(img.as<bf16>(), R, ukv, e, st, true);
+  }
+
+  // one decode step for `rows` rows; every kernel reads the step index from device memory.
+  // logits_out != null: lm_head stores fp32 logits there instead of the fused arg-max.
+  int decode_step(int rows, const dec::GreedyState& g, float* logits_out, cudaStream_t st) {
+    const int before = static_cast<int>(launches);
+    const int* sp = step.as<int>();
+    dec::embed_kernel<<<rows, 256, 0, st>>>(wte_f32, g.ids, g.ids_ld, sp, h.as<float>());
+    KERNEL_CHECK();
+    ++launches;
+    const int ln_grid = ceil_div(rows, 8);
+    for (int l = 0; l < NLAYER; ++l) {
+      const LayerW& L = layers[l];
+      dec::layernorm_kernel<<<ln_grid, 256, 0, st>>>(h.as<float>(), L.ln1_g, L.ln1_b, x.as<bf16>(), rows);
+      KERNEL_CHECK();
+      EpiQkvAppend eq{q.as<bf16>(), L.attn.bias, kv_geom(), l, sp};
+      gemm(x.as<bf16>(), rows, L.attn, eq, st, true);
+      dec::attention_kernel<<<ceil_div(rows * 16, 4), 128, 0, st>>>(q.as<bf16>(), kv_geom(), l, sp, attn_o.as<bf16>(), rows);
+      KERNEL_CHECK();
+      gemm(attn_o.as<bf16>(), rows, L.proj, store_f32(h.as<float>(), L.proj.bias, DM, ACT_NONE, h.as<float>()), st, true);
+      dec::layernorm_kernel<<<ln_grid, 256, 0, st>>>(h.as<float>(), L.ln2_g, L.ln2_b, x.as<bf16>(), rows);
+      KERNEL_CHECK();
+      gemm(x.as<bf16>(), rows, L.fc, store_bf16(mlp_mid.as<bf16>(), L.fc.bias, 4 * DM, ACT_GELU_NEW), st, true);
+      gemm(mlp_mid.as<bf16>(), rows, L.mproj, store_f32(h.as<float>(), L.mproj.bias, DM, ACT_NONE, h.as<float>()), st, true);
+      launches += 3;
+    }
+    dec::layernorm_kernel<<<ln_grid, 256, 0, st>>>(h.as<float>(), lnf_g, lnf_b, x.as<bf16>(), rows);
+    KERNEL_CHECK();
+    ++launches;
+    if (logits_out || opt_gemm_impl == 2) {
+      float* dst = logits_out ? logits_out : logits_tmp.as<float>();
+      gemm(x.as<bf16>(), rows, lm_head, store_f32(dst, nullptr, VOCAB, ACT_NONE), st, true);
+      dec::greedy_update_kernel<<<1, 1024, 0, st>>>(nullptr, nullptr, 0, dst, g, rows);
+    } else {
+      const int n_tiles = ceil_div(VOCAB, 128);
+      EpiArgmaxPartial ea{part_val.as<float>(), part_idx.as<int>(), n_tiles};
+      gemm(x.as<bf16>(), rows, lm_head, ea, st, true, 128);
+      dec::greedy_update_kernel<<<1, 1024, 0, st>>>(part_val.as<float>(), part_idx.as<int>(), n_tiles, nullptr, g, rows);
+    }
+    KERNEL_CHECK();
+    ++launches;
+    return static_cast<int>(launches) - before;
+  }
+
+  // greedy decode of `R` rows whose features sit in feats_bf16; host ids [R, max_length], returns reference width
+  int run_greedy(const bf16* feats_bf16, int R, int max_length, int32_t* out_ids, cudaStream_t st) {
+    ensure_decoder_ws(R, max_length);
+    if (opt_gemm_impl == 2) logits_tmp.ensure(static_cast<size_t>(R) * VOCAB * 4);
+    lm_prologue(feats_bf16, R, 1, st);
+    dec::GreedyState g{};
+    g.ids = ids.as<int>();
+    g.ids_ld = max_length;
+    g.unfinished = unfinished.as<int>();
+    g.unfinished_count = unf_count.as<int>();
+    g.step_ptr = step.as<int>();
+    dec::greedy_init_kernel<<<ceil_div(R, 256), 256, 0, st>>>(g, R);
+    KERNEL_CHECK();
+    ++launches;
+    const int steps = max_length - 1;
+    cudaGraphExec_t exec = nullptr;
+    int nodes = 0;
+    const int graph_key = R * 4096 + max_length;
+    // step 0 always runs eagerly (it also makes sure every kernel is loaded and configured before a capture)
+    decode_step(R, g, nullptr, st);
+    if (opt_cuda_graph && steps > 1) {
+      auto it = step_graphs.find(graph_key);
+      if (it == step_graphs.end()) {
+        cudaGraph_t graph;
+        const int64_t saved = launches;
+        CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        try {
+          nodes = decode_step(R, g, nullptr, st);
+        } catch (...) {
+          cudaGraph_t dead;
+          cudaStreamEndCapture(st, &dead);
+          throw;
+        }
+        CUDA_CHECK(cudaStreamEndCapture(st, &graph));
+        launches = saved;
+        CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+        CUDA_CHECK(cudaGraphDestroy(graph));
+        step_graphs[graph_key] = exec;
+        step_graph_nodes[graph_key] = nodes;
+      } else {
+        exec = it->second;
+        nodes = step_graph_nodes[graph_key];
+      }
+    }
+    int done_steps = 1;
+    std::vector<int> counts(steps > 0 ? steps : 1);
+    for (int t = 1; t < steps; ++t) {
+      if (exec) {
+        CUDA_CHECK(cudaGraphLaunch(exec, st));
+        launches += nodes;
+      } else {
+        decode_step(R, g, nullptr, st);
+      }
+      ++done_steps;
+      if ((t & 7) == 7 && t + 1 < steps) {  // early exit without a per-step sync (language_model.py:649)
+        int c = 1;
+        CUDA_CHECK(cudaMemcpyAsync(&c, unf_count.as<int>() + t, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (c == 0) break;
+      }
+    }
+    std::vector<int32_t> tmp(static_cast<size_t>(R) * max_length);
+    CUDA_CHECK(cudaMemcpyAsync(tmp.data(), ids.as<int>(), tmp.size() * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(counts.data(), unf_count.as<int>(), static_cast<size_t>(done_steps) * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    // the reference stops right after the first step that leaves no row unfinished (language_model.py:649)
+    int width = done_steps + 1;
+    for (int t = 0; t < done_steps; ++t) {
+      if (counts[t] == 0) {
+        width = t + 2;
+        break;
+      }
+    }
+    for (int r = 0; r < R; ++r) {
+      for (int c = 0; c < max_length; ++c)
+        out_ids[static_cast<size_t>(r) * max_length + c] = c < width ? tmp[static_cast<size_t>(r) * max_length + c] : RGRG_EOS;
+    }
+    return width;
+  }
+};
+
+// ====================================================================================================================
+// C ABI
+// ====================================================================================================================
+static std::string g_create_error;
+
+#define RGRG_TRY(e, ...)                                          \
+  try {                                                           \
+    CUDA_CHECK(cudaSetDevice((e)->device));                       \
+    __VA_ARGS__;                                                  \
+    return 0;                                                     \
+  } catch (const CudaError& ex) {                                 \
+    (e)->err = ex.what();                                         \
+    return ex.code == cudaErrorMemoryAllocation ? 2 : 1;          \
+  } catch (const std::exception& ex) {                            \
+    (e)->err = ex.what();                                         \
+    return 1;                                                     \
+  }
+
+extern "C" {
+
+const char* rgrg_version(void) { return "rgrg_b200 0.1 (sm_100a)"; }
+
+int rgrg_create(int device, rgrg_engine_t** out) {
+  try {
+    int n = 0;
+    CUDA_CHECK(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) throw std::runtime_error("no such CUDA device: " + std::to_string(device));
+    CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) throw std::runtime_error("rgrg_b200 requires a Blackwell (sm_100a) GPU; there is no fallback path");
+    rgrg_engine* e = new rgrg_engine();
+    e->device = device;
+    const char* ic = getenv("RGRG_IMPLICIT_CONV");
+    if (ic) e->opt_implicit_conv = atoi(ic);
+    *out = e;
+    return 0;
+  } catch (const std::exception& ex) {
+    g_create_error = ex.what();
+    return 1;
+  }
+}
+
+void rgrg_destroy(rgrg_engine_t* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  delete e;
+}
+
+const char* rgrg_last_error(const rgrg_engine_t* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int64_t rgrg_kernel_launches(const rgrg_engine_t* e) { return e->launches; }
+
+int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
+  const std::string k(key);
+  if (k == "implicit_conv") e->opt_implicit_conv = value;
+  else if (k == "cuda_graph") e->opt_cuda_graph = value;
+  else if (k == "gemm_impl") e->opt_gemm_impl = value;
+  else {
+    e->err = "unknown option: " + k;
+    return 1;
+  }
+  return 0;
+}
+
+int rgrg_load_weight(rgrg_engine_t* e, const char* name, const float* host_data, const int64_t* shape, int ndim) {
+  HostRef r;
+  r.p = host_data;
+  r.shape.assign(shape, shape + ndim);
+  e->host[name] = r;
+  return 0;
+}
+
+int rgrg_finalize_weights(rgrg_engine_t* e) { RGRG_TRY(e, e->finalize()); }
+
+static const float* stage_images(rgrg_engine* e, const float* images, int on_host, int B, int S, cudaStream_t st) {
+  if (!on_host) return images;
+  e->ensure_detector_ws(B, S);
+  CUDA_CHECK(cudaMemcpyAsync(e->images.p, images, static_cast<size_t>(B) * S * S * 4, cudaMemcpyHostToDevice, st));
+  return e->images.as<float>();
+}
+
+static void read_detections(rgrg_engine* e, int B, uint8_t* out_selected, uint8_t* out_detected, float* out_boxes,
+                            float* out_scores, float* out_trf, int32_t* out_top_idx, int32_t* out_np, cudaStream_t st) {
+  const size_t rows = static_cast<size_t>(B) * NREG;
+  if (out_selected) CUDA_CHECK(cudaMemcpyAsync(out_selected, e->selected.p, rows, cudaMemcpyDeviceToHost, st));
+  if (out_detected) CUDA_CHECK(cudaMemcpyAsync(out_detected, e->detected.p, rows, cudaMemcpyDeviceToHost, st));
+  if (out_boxes) CUDA_CHECK(cudaMemcpyAsync(out_boxes, e->top_boxes.p, rows * 16, cudaMemcpyDeviceToHost, st));
+  if (out_scores) CUDA_CHECK(cudaMemcpyAsync(out_scores, e->top_scores.p, rows * 4, cudaMemcpyDeviceToHost, st));
+  if (out_trf) CUDA_CHECK(cudaMemcpyAsync(out_trf, e->trf.p, rows * 1024 * 4, cudaMemcpyDeviceToHost, st));
+  if (out_top_idx) CUDA_CHECK(cudaMemcpyAsync(out_top_idx, e->top_idx.p, rows * 4, cudaMemcpyDeviceToHost, st));
+  if (out_np) CUDA_CHECK(cudaMemcpyAsync(out_np, e->prop_count.p, static_cast<size_t>(B) * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+static void check_ready(rgrg_engine* e) {
+  if (!e->weights_ready) throw std::runtime_error("weights not loaded: call rgrg_finalize_weights first");
+}
+
+int rgrg_detect(rgrg_engine_t* e, const float* images, int images_on_host, int B, int S, uint8_t* out_selected,
+                uint8_t* out_detected, float* out_boxes, float* out_scores, float* out_region_features,
+                int32_t* out_top_idx, int32_t* out_num_proposals, int* out_R, void* stream) {
+  RGRG_TRY(e, {
+    check_ready(e);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float* img = stage_images(e, images, images_on_host, B, S, st);
+    const int R = e->run_detect(img, B, S, st);
+    if (out_R) *out_R = R;
+    read_detections(e, B, out_selected, out_detected, out_boxes, out_scores, out_region_features, out_top_idx,
+                    out_num_proposals, st);
+  });
+}
+
+int rgrg_generate(rgrg_engine_t* e, const float* images, int images_on_host, int B, int S, int max_length,
+                  int num_beams, int early_stopping, int32_t* out_ids, int* out_width, uint8_t* out_selected,
+                  uint8_t* out_detected, float* out_boxes, float* out_scores, int* out_R, void* stream) {
+  RGRG_TRY(e, {
+    check_ready(e);
+    if (num_beams != 1) throw std::runtime_error("beam search is not available in this build (num_beams must be 1)");
+    if (max_length < 2 || max_length > 1024) throw std::runtime_error("max_length must be in [2, 1024]");
+    (void)early_stopping;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float* img = stage_images(e, images, images_on_host, B, S, st);
+    const int R = e->run_detect(img, B, S, st);
+    *out_R = R;
+    int width = 0;
+    if (R > 0) width = e->run_greedy(e->lm_in.as<bf16>(), R, max_length, out_ids, st);
+    if (out_width) *out_width = width;
+    read_detections(e, B, out_selected, out_detected, out_boxes, out_scores, nullptr, nullptr, nullptr, st);
+  });
+}
+
+static const bf16* stage_feats(rgrg_engine* e, const float* feats, int on_host, int R, cudaStream_t st) {
+  e->trf.ensure(static_cast<size_t>(R) * 1024 * 4);
+  e->lm_in.ensure(static_cast<size_t>(R) * 1024 * 2);
+  const float* src = feats;
+  if (on_host) {
+    CUDA_CHECK(cudaMemcpyAsync(e->trf.p, feats, static_cast<size_t>(R) * 1024 * 4, cudaMemcpyHostToDevice, st));
+    src = e->trf.as<float>();
+  }
+  det::cast_bf16_kernel<<<rgrg_engine::grid_for(static_cast<long long>(R) * 1024), 256, 0, st>>>(src, e->lm_in.as<bf16>(),
+                                                                                             static_cast<long long>(R) * 1024);
+  KERNEL_CHECK();
+  ++e->launches;
+  return e->lm_in.as<bf16>();
+}
+
+int rgrg_lm_generate(rgrg_engine_t* e, const float* feats, int feats_on_host, int R, int max_length, int num_beams,
+                     int early_stopping, int32_t* out_ids, int* out_width, void* stream) {
+  RGRG_TRY(e, {
+    check_ready(e);
+    if (num_beams != 1) throw std::runtime_error("beam search is not available in this build (num_beams must be 1)");
+    if (max_length < 2 || max_length > 1024) throw std::runtime_error("max_length must be in [2, 1024]");
+    if (R <= 0) throw std::runtime_error("R must be positive");
+    (void)early_stopping;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bf16* f = stage_feats(e, feats, feats_on_host, R, st);
+    const int width = e->run_greedy(f, R, max_length, out_ids, st);
+    if (out_width) *out_width = width;
+  });
+}
+
+int rgrg_lm_forced_logits(rgrg_engine_t* e, const float* feats_dev, int R, const int32_t* forced_ids_dev, int n_tokens,
+                          float* out_logits_dev, void* stream) {
+  RGRG_TRY(e, {
+    check_ready(e);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bf16* f = stage_feats(e, feats_dev, 0, R, st);
+    e->ensure_decoder_ws(R, n_tokens + 1);
+    e->lm_prologue(f, R, 1, st);
+    dec::GreedyState g{};
+    g.ids = e->ids.as<int>();
+    g.ids_ld = n_tokens;
+    g.unfinished = e->unfinished.as<int>();
+    g.unfinished_count = e->unf_count.as<int>();
+    g.step_ptr = e->step.as<int>();
+    g.forced = forced_ids_dev;
+    dec::greedy_init_kernel<<<ceil_div(R, 256), 256, 0, st>>>(g, R);
+    KERNEL_CHECK();
+    ++e->launches;
+    for (int t = 0; t < n_tokens; ++t) e->decode_step(R, g, out_logits_dev + static_cast<size_t>(t) * R * VOCAB, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int rgrg_rpn_filter(rgrg_engine_t* e, const float* objectness_dev, const float* deltas_dev, const float* decoded_dev, int B,
+                    int feat, int image_size, float* boxes_dev, float* scores_dev, int32_t* count_dev,
+                    int32_t* topk_idx_dev, int32_t* keep_rank_dev, void* stream) {
+  RGRG_TRY(e, {
+    check_ready(e);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long N = static_cast<long long>(feat) * feat * det::NUM_ANCHORS;
+    det::RpnIn in{};
+    in.obj = objectness_dev;
+    in.obj_bs = N;
+    in.obj_ps = det::NUM_ANCHORS;
+    in.deltas = deltas_dev;
+    in.del_bs = N * 4;
+    in.del_ps = det::NUM_ANCHORS * 4;
+    in.decoded = decoded_dev;
+    det::RpnOut out{boxes_dev, scores_dev, count_dev, topk_idx_dev, keep_rank_dev};
+    e->run_rpn_filter(in, out, B, feat, image_size, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int rgrg_roi_align(rgrg_engine_t* e, const void* feats_bf16_dev, const float* boxes_dev, const int32_t* count_dev, int B,
+                   int feat, int C, int image_size, void* out_bf16_dev, void* stream) {
+  RGRG_TRY(e, {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (C % 8) throw std::runtime_error("C must be a multiple of 8");
+    e->roi_off.ensure(static_cast<size_t>(B + 1) * 4);
+    det::roi_offsets_kernel<<<1, 32, 0, st>>>(count_dev, e->roi_off.as<int>(), B);
+    const float scale = exp2f(roundf(log2f(static_cast<float>(feat) / static_cast<float>(image_size))));
+    det::roi_align_kernel<<<dim3(TOPK, B), 256, 0, st>>>(static_cast<const bf16*>(feats_bf16_dev), boxes_dev, count_dev,
+                                                        e->roi_off.as<int>(), static_cast<bf16*>(out_bf16_dev), feat, C, scale);
+    KERNEL_CHECK();
+    e->launches += 2;
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int rgrg_roi_tail(rgrg_engine_t* e, const float* class_logits_dev, const float* box_regression_dev, const float* boxes_dev,
+                  const int32_t* count_dev, int B, int image_size, uint8_t* detected_dev, int32_t* top_idx_dev,
+                  float* scores_dev, float* top_boxes_dev, void* stream) {
+  RGRG_TRY(e, {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    e->roi_off.ensure(static_cast<size_t>(B + 1) * 4);
+    det::roi_offsets_kernel<<<1, 32, 0, st>>>(count_dev, e->roi_off.as<int>(), B);
+    det::RoiTailOut to{detected_dev, top_idx_dev, scores_dev, top_boxes_dev};
+    det::roi_tail_kernel<<<B, 256, 0, st>>>(class_logits_dev, 30, box_regression_dev, 120, boxes_dev, count_dev,
+                                            e->roi_off.as<int>(), to, image_size);
+    KERNEL_CHECK();
+    e->launches += 2;
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int rgrg_gemm_bf16(rgrg_engine_t* e, const void* A_dev, const void* W_dev, const float* bias_dev, int M, int N, int K, int act,
+                   int impl, float* out_dev, void* stream) {
+  RGRG_TRY(e, {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Linear L;
+    L.w = static_cast<bf16*>(const_cast<void*>(W_dev));
+    L.bias = const_cast<float*>(bias_dev);
+    L.N = N;
+    L.K = K;
+    EpiStore ep = rgrg_engine::store_f32(out_dev, bias_dev, N, act);
+    const int saved = e->opt_gemm_impl;
+    e->opt_gemm_impl = impl == 2 ? 2 : 0;
+    try {
+      if (impl != 2) L.make_maps();
+      e->gemm(static_cast<const bf16*>(A_dev), M, L, ep, st, true, impl == 0 ? 128 : (impl == 1 ? 64 : 0));
+    } catch (...) {
+      e->opt_gemm_impl = saved;
+      throw;
+    }
+    e->opt_gemm_impl = saved;
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int rgrg_conv3x3_bf16(rgrg_engine_t* e, const void* in_dev, const void* w_dev, const float* bias_dev, int B, int H, int W,
+                      int Cin, int Cout, int relu, int implicit, float* out_dev, void* stream) {
+  RGRG_TRY(e, {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Linear L;
+    L.w = static_cast<bf16*>(const_cast<void*>(w_dev));
+    L.bias = const_cast<float*>(bias_dev);
+    L.N = Cout;
+    L.K = 9 * Cin;
+    L.make_maps();
+    EpiStore ep = rgrg_engine::store_f32(out_dev, bias_dev, Cout, relu ? ACT_RELU : ACT_NONE);
+    const int saved = e->opt_implicit_conv;
+    e->opt_implicit_conv = implicit;
+    try {
+      e->conv3x3(static_cast<const bf16*>(in_dev), B, H, W, Cin, 1, L, ep, st);
+    } catch (...) {
+      e->opt_implicit_conv = saved;
+      throw;
+    }
+    e->opt_implicit_conv = saved;
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int rgrg_backbone(rgrg_engine_t* e, const float* images_dev, int B, int S, void* out_feats_bf16_dev, void* stream) {
+  RGRG_TRY(e, {
+    check_ready(e);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    e->ensure_detector_ws(B, S);
+    e->run_backbone(images_dev, B, S, static_cast<bf16*>(out_feats_bf16_dev), st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst, size_t bytes) {
+  RGRG_TRY(e, {
+    const std::string n(name);
+    const DevBuf* b = nullptr;
+    if (n == "rpn_out") b = &e->rpn_out;
+    else if (n == "features") b = &e->feats;
+    else if (n == "pred_out") b = &e->pred_out;
+    else if (n == "proposals") b = &e->prop_boxes;
+    else if (n == "proposal_scores") b = &e->prop_scores;
+    else if (n == "selection_logits") b = &e->sel_logits;
+    else if (n == "region_features_2048") b = &e->mean2048;
+    else if (n == "fc7") b = &e->f7;
+    else throw std::runtime_error("unknown debug buffer: " + n);
+    if (bytes > b->bytes) throw std::runtime_error("debug read larger than buffer: " + n);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(host_dst, b->p, bytes, cudaMemcpyDeviceToHost));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,130 @@
+"""Host-side mirror of the reference's inference surface, backed by the C-ABI engine.
+
+    model = ReportGenerationModel(pretrain_without_lm_model=True)          # report_generation_model.py:21-33
+    model.load_state_dict(checkpoint["model"]); model.to(device); model.eval()  # generate_reports_for_images.py:160-163
+    output = model.generate(images, max_length=..., num_beams=..., early_stopping=...)  # :109-114
+
+`generate()` keeps the reference's signature, return tuple, `-1` sentinel and error behaviour
+(report_generation_model.py:212-276; language_model.py:428-479).  Everything numeric happens inside
+librgrg_b200.so; this file only converts buffers to the tensors the reference's callers expect.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from .engine import Engine
+
+
+def _check_generation_mode(max_length, num_beams, num_beam_groups, do_sample, num_return_sequences):
+    """language_model.py:422-479: same mode dispatch, same exception types and messages."""
+    is_greedy = (num_beams == 1) and (num_beam_groups == 1) and do_sample is False
+    is_sample = (num_beams == 1) and (num_beam_groups == 1) and do_sample is True
+    is_beam = (num_beams > 1) and (num_beam_groups == 1) and do_sample is False
+    is_beam_sample = (num_beams > 1) and (num_beam_groups == 1) and do_sample is True
+    is_group_beam = (num_beams > 1) and (num_beam_groups > 1)
+    if num_beam_groups > num_beams:
+        raise ValueError("'num_beam_groups' has to be smaller or equal to 'num_beams'")
+    if is_group_beam and do_sample is True:
+        raise ValueError("Diverse beam search cannot be used in sampling mode. Make sure that 'do_sample' is set to 'False'.")
+    if is_greedy:
+        if num_return_sequences > 1:
+            raise ValueError(f"num_return_sequences has to be 1, but is {num_return_sequences} when doing greedy search.")
+        return "greedy"
+    if is_sample:
+        raise NotImplementedError("Multinomial sampling is not implemented.")
+    if is_beam:
+        if num_return_sequences > num_beams:
+            raise ValueError("'num_return_sequences' has to be smaller or equal to 'num_beams'.")
+        if max_length is None:
+            raise ValueError("max_length has to be set for beam generation.")
+        return "beam"
+    if is_beam_sample:
+        raise NotImplementedError("Beam-search multinomial sampling is not implemented.")
+    if is_group_beam:
+        raise NotImplementedError("Diverse beam-search decoding is not implemented.")
+    raise ValueError("unsupported generation mode")
+
+
+class LanguageModel:
+    """Mirror of src/language_model/language_model.py `LanguageModel.generate` (the entry
+    evaluate_bbox_variations.py:131-136 calls directly)."""
+
+    def __init__(self, owner: "ReportGenerationModel"):
+        self._owner = owner
+
+    @torch.no_grad()
+    def generate(self, image_hidden_states, max_length=None, num_beams=1, num_beam_groups=1, do_sample=False,
+                 num_return_sequences=1, early_stopping=False) -> torch.LongTensor:
+        _check_generation_mode(max_length, num_beams, num_beam_groups, do_sample, num_return_sequences)
+        if max_length is None:
+            max_length = 1024  # the reference would decode until every row emits EOS; positions end at 1024
+        ids = self._owner._engine().lm_generate(image_hidden_states, int(max_length), int(num_beams), bool(early_stopping))
+        return torch.from_numpy(ids.astype(np.int64)).to(self._owner.device)
+
+
+class ReportGenerationModel:
+    def __init__(self, pretrain_without_lm_model: bool = False, device: Optional[torch.device] = None):
+        self.pretrain_without_lm_model = pretrain_without_lm_model
+        self.device = torch.device(device) if device is not None else torch.device("cuda", 0)
+        self.training = False
+        self._eng: Optional[Engine] = None
+        self._state_dict: Optional[Dict[str, torch.Tensor]] = None
+        self.language_model = LanguageModel(self)
+
+    # ---- nn.Module-flavoured plumbing the reference's script uses (generate_reports_for_images.py:160-163)
+    def load_state_dict(self, state_dict, strict: bool = True):
+        self._state_dict = state_dict
+        if self._eng is not None:
+            self._eng.close()
+            self._eng = None
+        return self
+
+    def to(self, device, non_blocking: bool = False):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("rgrg_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if self._eng is not None and device != self.device:
+            self._eng.close()
+            self._eng = None
+        self.device = device if device.index is not None else torch.device("cuda", torch.cuda.current_device())
+        return self
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("rgrg_b200 is an inference engine (the training path is out of scope)")
+        return self
+
+    def _engine(self) -> Engine:
+        if self._eng is None:
+            if self._state_dict is None:
+                raise RuntimeError("load_state_dict() must be called before generate()")
+            eng = Engine(self.device.index or 0)
+            eng.load_state_dict(self._state_dict)
+            self._eng = eng
+        return self._eng
+
+    @torch.no_grad()
+    def generate(self, images, max_length: int = None, num_beams: int = 1, num_beam_groups: int = 1,
+                 do_sample: bool = False, num_return_sequences: int = 1, early_stopping: bool = False):
+        """report_generation_model.py:212-276.  Returns (output_ids int64 [R, T'], selected_regions bool [B,29],
+        detections {"top_region_boxes" [B,29,4], "top_scores" [B,29]}, class_detected bool [B,29]) or -1."""
+        _check_generation_mode(max_length, num_beams, num_beam_groups, do_sample, num_return_sequences)
+        if max_length is None:
+            max_length = 1024
+        out = self._engine().generate(images, int(max_length), int(num_beams), bool(early_stopping))
+        if out["R"] == 0:
+            return -1
+        dev = self.device
+        output_ids = torch.from_numpy(out["ids"].astype(np.int64)).to(dev)
+        selected_regions = torch.from_numpy(out["selected"]).to(dev)
+        detections = {"top_region_boxes": torch.from_numpy(out["boxes"]).to(dev),
+                      "top_scores": torch.from_numpy(out["scores"]).to(dev)}
+        class_detected = torch.from_numpy(out["detected"]).to(dev)
+        return output_ids, selected_regions, detections, class_detected

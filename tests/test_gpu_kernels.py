@@ -1,0 +1,127 @@
+"""-m gpu: kernel-level parity through the C ABI — tcgen05 GEMM / implicit conv against fp32 torch math, and the
+integer / boolean detector stages bit-exact against vectors the UNMODIFIED reference produced (tests/golden)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+T = torch.from_numpy
+
+
+@pytest.fixture(scope="module")
+def eng_bare():
+    from rgrg_b200 import Engine
+
+    return Engine(0)
+
+
+def _rand_bf16(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).cuda()
+
+
+@pytest.mark.parametrize("impl", [2, 0, 1])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (300, 200, 192), (928, 3072, 1024), (37, 800, 2048),
+                                   (257, 50257, 1024), (1000, 64, 576)])
+def test_gemm_matches_fp32_math(eng_bare, impl, M, N, K):
+    A = _rand_bf16((M, K), 1)
+    W = _rand_bf16((N, K), 2, 0.05)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(3)).cuda()
+    out = eng_bare.gemm(A, W, bias, act=0, impl=impl)
+    ref = A.float() @ W.float().T + bias
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), "max abs err %g" % err
+
+
+@pytest.mark.parametrize("act", [1, 2])
+def test_gemm_epilogue_activations(eng_bare, act):
+    A = _rand_bf16((200, 128), 4)
+    W = _rand_bf16((256, 128), 5, 0.1)
+    out = eng_bare.gemm(A, W, None, act=act, impl=0)
+    ref = A.float() @ W.float().T
+    ref = torch.relu(ref) if act == 1 else 0.5 * ref * (1 + torch.tanh(0.7978845608028654 * (ref + 0.044715 * ref ** 3)))
+    assert (out - ref).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("implicit", [False, True])
+@pytest.mark.parametrize("B,H,Cin,Cout", [(2, 16, 64, 64), (1, 32, 128, 128), (2, 16, 2048, 256), (1, 128, 64, 64)])
+def test_conv3x3_matches_torch(eng_bare, implicit, B, H, Cin, Cout):
+    x = _rand_bf16((B, H, H, Cin), 6)
+    w = _rand_bf16((Cout, 3, 3, Cin), 7, 0.05)  # tap-major K
+    bias = torch.randn(Cout, generator=torch.Generator().manual_seed(8)).cuda()
+    out = eng_bare.conv3x3(x, w.reshape(Cout, -1), bias, relu=True, implicit=implicit)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), bias, padding=1)
+    ref = torch.relu(ref).permute(0, 2, 3, 1)
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), "max abs err %g" % err
+
+
+# ---- detector integer stages: need the engine's constant tables -> weights loaded once per module
+@pytest.fixture(scope="module")
+def eng(synth_sd):
+    from rgrg_b200 import Engine
+
+    e = Engine(0)
+    e.load_state_dict(synth_sd)
+    return e
+
+
+def test_rpn_filter_bit_exact_on_reference_vectors(eng, golden):
+    g = golden("rpn_filter.npz")
+    obj = T(g["objectness"]).cuda()
+    boxes, scores, count, topk, keep = eng.rpn_filter(obj, decoded=T(g["decoded"]).cuda())
+    assert count.cpu().tolist() == list(g["count"])
+    ref_topk = torch.topk(T(g["objectness"]), 1000, dim=1).indices
+    assert torch.equal(topk.cpu().long(), ref_topk)
+    for b in range(2):
+        n = int(g["count"][b])
+        assert torch.equal(boxes[b, :n].cpu(), T(g["boxes%d" % b]))
+        assert torch.allclose(scores[b, :n].cpu(), T(g["scores%d" % b]), rtol=0, atol=1e-6)
+
+
+def test_rpn_decode_on_device_matches_reference(eng, golden):
+    g = golden("rpn_filter.npz")
+    boxes, scores, count, topk, keep = eng.rpn_filter(T(g["objectness"]).cuda(), deltas=T(g["deltas"]).cuda())
+    # device expf differs from the CPU's by <= 2 ulp: boxes agree to 1e-3 px, the keep list may differ only at IoU ties
+    dec = T(g["decoded"])
+    for b in range(2):
+        n = int(count[b])
+        sel = topk[b, keep[b, :n].long()].cpu().long()
+        mine = boxes[b, :n].cpu()
+        ref = dec[b, sel].clamp(0, 512)
+        assert (mine - ref).abs().max().item() < 1e-3
+        assert abs(n - int(g["count"][b])) <= 2
+
+
+def test_roi_align_matches_reference_kernel(eng, golden):
+    g = golden("roi_align.npz")
+    feats = T(g["feats"]).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()  # NHWC
+    rois = [T(g["rois0"]), T(g["rois1"])]
+    boxes = torch.zeros(2, 1000, 4)
+    for b in range(2):
+        boxes[b, : rois[b].shape[0]] = rois[b]
+    count = torch.tensor([r.shape[0] for r in rois], dtype=torch.int32)
+    out = eng.roi_align(feats, boxes.cuda(), count.cuda())  # [P, 64 bins, C]
+    import torchvision
+
+    ref = torchvision.ops.roi_align(feats.float().permute(0, 3, 1, 2).cpu(), rois, (8, 8), 1.0 / 32, 2)  # bf16-rounded input
+    ref = ref.permute(0, 2, 3, 1).reshape(ref.shape[0], 64, -1)
+    err = (out.float().cpu() - ref).abs().max().item()
+    assert err < 0.02 * max(1.0, ref.abs().max().item())  # bf16 output rounding
+    # and against the reference's fp32 output, looser (input + output rounding)
+    ref32 = T(g["pooled"]).permute(0, 2, 3, 1).reshape(ref.shape[0], 64, -1)
+    assert (out.float().cpu() - ref32).abs().max().item() < 0.03 * max(1.0, ref32.abs().max().item())
+
+
+def test_roi_tail_bit_exact_on_reference_vectors(eng, golden):
+    g = golden("roi_tail.npz")
+    props = [T(g["proposals0"]), T(g["proposals1"])]
+    boxes = torch.zeros(2, 1000, 4)
+    for b in range(2):
+        boxes[b, : props[b].shape[0]] = props[b]
+    count = torch.tensor([p.shape[0] for p in props], dtype=torch.int32)
+    det, idx, scores, tb = eng.roi_tail(T(g["class_logits"]).cuda(), T(g["box_regression"]).cuda(), boxes.cuda(), count.cuda())
+    assert torch.equal(det.cpu(), T(g["class_detected"]))
+    assert torch.equal(idx.cpu().long(), T(g["top_idx"]))
+    assert torch.allclose(scores.cpu(), T(g["top_scores"]), rtol=1e-5, atol=1e-7)
+    assert torch.allclose(tb.cpu(), T(g["top_region_boxes"]), rtol=0, atol=2e-3)
