@@ -123,8 +123,12 @@ RGRG_API int rgrg_backbone(rgrg_engine_t* e, const float* images_dev, int B, int
  * "features" bf16 [B,f,f,2048], "pred_out" fp32 [P,150], "proposals" fp32 [B,1000,4], "selection_logits" fp32 [B*29] */
 RGRG_API int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst, size_t bytes);
 
-/* behaviour switches: "implicit_conv" (0/1), "cuda_graph" (0/1), "gemm_impl" (0 tcgen05, 2 CUDA-core cross-check) */
+/* behaviour switches: "implicit_conv" (0/1), "cuda_graph" (0/1), "gemm_impl" (0 tcgen05, 2 CUDA-core cross-check),
+ * "profile" (0/1: record CUDA events around every kernel category on the launch stream; disables graph replay) */
 RGRG_API int rgrg_set_option(rgrg_engine_t* e, const char* key, int value);
+
+/* per-category device time since "profile" was switched on: text lines "<category> <total ms> <launches>\n" */
+RGRG_API int rgrg_profile_read(rgrg_engine_t* e, char* buf, size_t buflen);
 
 /* counters since creation: kernels launched by this library (bench.py's gpu_launches claim) */
 RGRG_API int64_t rgrg_kernel_launches(const rgrg_engine_t* e);

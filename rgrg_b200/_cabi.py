@@ -30,6 +30,7 @@ _PROTOTYPES = {
     "rgrg_backbone": (_i, [c_p, c_p, _i, _i, c_p, c_p]),
     "rgrg_debug_read": (_i, [c_p, C.c_char_p, c_p, C.c_size_t]),
     "rgrg_set_option": (_i, [c_p, C.c_char_p, _i]),
+    "rgrg_profile_read": (_i, [c_p, C.c_char_p, C.c_size_t]),
     "rgrg_kernel_launches": (C.c_int64, [c_p]),
 }
 

@@ -90,12 +90,84 @@ struct LayerW {
 
 }  // namespace
 
+struct rgrg_engine;
+struct ProfScope {
+  rgrg_engine* e;
+  cudaStream_t st;
+  int rec;
+  ProfScope(rgrg_engine* e, const char* tag, cudaStream_t st);
+  ~ProfScope();
+};
+
 struct rgrg_engine {
+  // ---- optional per-category device timing (CUDA events on the launch stream; bench.py's roofline source)
+  struct ProfRec {
+    int cat;
+    cudaEvent_t a, b;
+  };
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_pool;
+  size_t prof_used = 0;
+  std::vector<ProfRec> prof_recs;
+  std::vector<std::string> prof_names;
+  std::map<std::string, int> prof_ids;
+  cudaEvent_t prof_event() {
+    if (prof_used == prof_pool.size()) {
+      cudaEvent_t ev;
+      CUDA_CHECK(cudaEventCreate(&ev));
+      prof_pool.push_back(ev);
+    }
+    return prof_pool[prof_used++];
+  }
+  int prof_cat(const char* tag) {
+    auto it = prof_ids.find(tag);
+    if (it != prof_ids.end()) return it->second;
+    const int id = static_cast<int>(prof_names.size());
+    prof_names.push_back(tag);
+    prof_ids[tag] = id;
+    return id;
+  }
+  std::string prof_report() {
+    CUDA_CHECK(cudaDeviceSynchronize());
+    std::vector<double> ms(prof_names.size(), 0.0);
+    std::vector<long long> cnt(prof_names.size(), 0);
+    for (const ProfRec& r : prof_recs) {
+      float t = 0.0f;
+      CUDA_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+      ms[r.cat] += t;
+      cnt[r.cat] += 1;
+    }
+    std::string out;
+    for (size_t i = 0; i < prof_names.size(); ++i) {
+      char line[256];
+      snprintf(line, sizeof(line), "%s %.6f %lld\n", prof_names[i].c_str(), ms[i], cnt[i]);
+      out += line;
+    }
+    return out;
+  }
+  void prof_reset() {
+    prof_recs.clear();
+    prof_used = 0;
+  }
+
   int device = 0;
+  // all work runs on an engine-owned non-blocking stream (the legacy default stream cannot be captured into a CUDA
+  // graph); it is ordered after the caller's stream on entry, and every entry point host-synchronises before returning
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev_enter = nullptr;
+  cudaStream_t enter(void* caller_stream) {
+    if (!own_stream) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaEventCreateWithFlags(&ev_enter, cudaEventDisableTiming));
+    }
+    CUDA_CHECK(cudaEventRecord(ev_enter, static_cast<cudaStream_t>(caller_stream)));
+    CUDA_CHECK(cudaStreamWaitEvent(own_stream, ev_enter, 0));
+    return own_stream;
+  }
   std::string err;
   int64_t launches = 0;
   bool weights_ready = false;
-  int opt_implicit_conv = 0;
+  int opt_implicit_conv = 1;
   int opt_cuda_graph = 1;
   int opt_gemm_impl = 0;
   std::unordered_map<std::string, HostRef> host;
@@ -128,6 +200,9 @@ struct rgrg_engine {
 
   ~rgrg_engine() {
     for (auto& g : step_graphs) cudaGraphExecDestroy(g.second);
+    for (cudaEvent_t ev : prof_pool) cudaEventDestroy(ev);
+    if (ev_enter) cudaEventDestroy(ev_enter);
+    if (own_stream) cudaStreamDestroy(own_stream);
     for (void* p : weight_allocs) cudaFree(p);
     DevBuf* all[] = {&images, &act[0], &act[1], &t1, &t2, &idb, &sub, &col, &feats, &rpn_t, &rpn_out, &prop_boxes,
                      &prop_scores, &prop_count, &roi_off, &pooled, &f6, &f7, &pred_out, &detected, &top_idx,
@@ -149,8 +224,10 @@ struct rgrg_engine {
   // GEMM dispatch
   // ================================================================================================================
   template <class Epi>
-  void gemm(const bf16* A, int M, const Linear& W, const Epi& epi, cudaStream_t st, bool m_fastest, int force_bn = 0) {
+  void gemm(const char* tag, const bf16* A, int M, const Linear& W, const Epi& epi, cudaStream_t st, bool m_fastest,
+            int force_bn = 0) {
     if (M <= 0) return;
+    ProfScope ps(this, tag, st);
     if (opt_gemm_impl == 2) {
       if constexpr (std::is_same<Epi, EpiArgmaxPartial>::value) {
         throw std::runtime_error("arg-max epilogue has no CUDA-core variant");
@@ -183,7 +260,9 @@ struct rgrg_engine {
 
   // 3x3 / stride 1 / pad 1 conv as implicit GEMM through a 4-D tensor map (K loop = 9 taps x Cin/64)
   template <class Epi>
-  void conv3x3_implicit(const bf16* in, int B, int H, int Wd, int Cin, const Linear& W, const Epi& epi, cudaStream_t st) {
+  void conv3x3_implicit(const char* tag, const bf16* in, int B, int H, int Wd, int Cin, const Linear& W, const Epi& epi,
+                        cudaStream_t st) {
+    ProfScope ps(this, tag, st);
     if (H % 8 || Wd % 16 || Cin % 64) throw std::runtime_error("implicit conv needs H%8==0, W%16==0, Cin%64==0");
     tc::GemmShape s{};
     s.M = B * H * Wd;
@@ -206,6 +285,7 @@ struct rgrg_engine {
   }
 
   void im2col(const bf16* in, bf16* colbuf, int B, int H, int Wd, int C, int stride, cudaStream_t st) {
+    ProfScope ps(this, "im2col", st);
     const int Ho = H / stride, Wo = Wd / stride;
     const size_t total = static_cast<size_t>(B) * Ho * Wo * 9 * (C / 8);
     const int grid = static_cast<int>(std::min<size_t>(ceil_div64(total, 256), 148 * 16));
@@ -215,14 +295,15 @@ struct rgrg_engine {
   }
 
   template <class Epi>
-  void conv3x3(const bf16* in, int B, int H, int Wd, int Cin, int stride, const Linear& W, const Epi& epi, cudaStream_t st) {
+  void conv3x3(const char* tag, const bf16* in, int B, int H, int Wd, int Cin, int stride, const Linear& W, const Epi& epi,
+               cudaStream_t st) {
     if (stride == 1 && opt_implicit_conv && opt_gemm_impl != 2) {
-      conv3x3_implicit(in, B, H, Wd, Cin, W, epi, st);
+      conv3x3_implicit(tag, in, B, H, Wd, Cin, W, epi, st);
     } else {
       const int Ho = H / stride, Wo = Wd / stride;
       col.ensure(static_cast<size_t>(B) * Ho * Wo * 9 * Cin * 2);
       im2col(in, col.as<bf16>(), B, H, Wd, Cin, stride, st);
-      gemm(col.as<bf16>(), B * Ho * Wo, W, epi, st, false);
+      gemm(tag, col.as<bf16>(), B * Ho * Wo, W, epi, st, false);
     }
   }
 
@@ -570,9 +651,12 @@ struct rgrg_engine {
   void run_backbone(const float* img_dev, int B, int S, bf16* out_feats, cudaStream_t st) {
     if (S % 128 != 0) throw std::runtime_error("image size must be a multiple of 128");
     const int P = S / 4;
-    det::stem_kernel<<<dim3(P / 8, P / 8, B), 256, 0, st>>>(img_dev, stem_w, stem_b, act[0].as<bf16>(), S);
-    KERNEL_CHECK();
-    ++launches;
+    {
+      ProfScope ps(this, "stem", st);
+      det::stem_kernel<<<dim3(P / 8, P / 8, B), 256, 0, st>>>(img_dev, stem_w, stem_b, act[0].as<bf16>(), S);
+      KERNEL_CHECK();
+      ++launches;
+    }
     int cur = 0, H = P;
     for (size_t i = 0; i < blocks.size(); ++i) {
       const BlockW& bw = blocks[i];
@@ -582,14 +666,15 @@ struct rgrg_engine {
       const int Ho = H / bw.stride;
       const int M_in = B * H * H, M_out = B * Ho * Ho;
       // conv1 1x1 + BN + ReLU
-      gemm(xin, M_in, bw.c1, store_bf16(t1.as<bf16>(), bw.c1.bias, bw.width, ACT_RELU), st, false);
+      gemm("conv1x1", xin, M_in, bw.c1, store_bf16(t1.as<bf16>(), bw.c1.bias, bw.width, ACT_RELU), st, false);
       // conv2 3x3 (stride here, v1.5) + BN + ReLU
-      conv3x3(t1.as<bf16>(), B, H, H, bw.width, bw.stride, bw.c2, store_bf16(t2.as<bf16>(), bw.c2.bias, bw.width, ACT_RELU), st);
+      conv3x3("conv3x3", t1.as<bf16>(), B, H, H, bw.width, bw.stride, bw.c2, store_bf16(t2.as<bf16>(), bw.c2.bias, bw.width, ACT_RELU), st);
       // identity / downsample branch
       const bf16* identity = xin;
       if (bw.has_ds) {
         const bf16* ds_in = xin;
         if (bw.stride == 2) {
+          ProfScope ps(this, "subsample", st);
           const size_t total = static_cast<size_t>(M_out) * (bw.cin / 8);
           det::subsample2_kernel<<<static_cast<int>(std::min<size_t>(ceil_div64(total, 256), 148 * 16)), 256, 0, st>>>(
               xin, sub.as<bf16>(), B, H, H, bw.cin);
@@ -597,17 +682,18 @@ struct rgrg_engine {
           ++launches;
           ds_in = sub.as<bf16>();
         }
-        gemm(ds_in, M_out, bw.ds, store_bf16(idb.as<bf16>(), bw.ds.bias, bw.cout, ACT_NONE), st, false);
+        gemm("conv1x1", ds_in, M_out, bw.ds, store_bf16(idb.as<bf16>(), bw.ds.bias, bw.cout, ACT_NONE), st, false);
         identity = idb.as<bf16>();
       }
       // conv3 1x1 + BN, + identity, ReLU
-      gemm(t2.as<bf16>(), M_out, bw.c3, store_bf16(yout, bw.c3.bias, bw.cout, ACT_RELU, identity), st, false);
+      gemm("conv1x1", t2.as<bf16>(), M_out, bw.c3, store_bf16(yout, bw.c3.bias, bw.cout, ACT_RELU, identity), st, false);
       cur ^= 1;
       H = Ho;
     }
   }
 
   void run_rpn_filter(const det::RpnIn& in, const det::RpnOut& out, int B, int feat, int S, cudaStream_t st) {
+    ProfScope ps(this, "rpn_topk_nms", st);
     det::rpn_proposals_kernel<<<B, det::RPN_THREADS, det::RPN_SMEM, st>>>(in, out, feat * feat * det::NUM_ANCHORS, feat, S, 0.7f);
     KERNEL_CHECK();
     ++launches;
@@ -619,8 +705,8 @@ struct rgrg_engine {
     const int f = S / 32;
     run_backbone(img_dev, B, S, feats.as<bf16>(), st);
     // RPN head: 3x3 conv + ReLU, then both 1x1 heads as one N = 160 + 640 GEMM with fp32 (decision-critical) output
-    conv3x3(feats.as<bf16>(), B, f, f, 2048, 1, rpn_conv, store_bf16(rpn_t.as<bf16>(), rpn_conv.bias, 2048, ACT_RELU), st);
-    gemm(rpn_t.as<bf16>(), B * f * f, rpn_heads, store_f32(rpn_out.as<float>(), rpn_heads.bias, 800, ACT_NONE), st, false);
+    conv3x3("rpn_conv", feats.as<bf16>(), B, f, f, 2048, 1, rpn_conv, store_bf16(rpn_t.as<bf16>(), rpn_conv.bias, 2048, ACT_RELU), st);
+    gemm("rpn_heads", rpn_t.as<bf16>(), B * f * f, rpn_heads, store_f32(rpn_out.as<float>(), rpn_heads.bias, 800, ACT_NONE), st, false);
     det::RpnIn in{};
     in.obj = rpn_out.as<float>();
     in.deltas = rpn_out.as<float>() + 160;
@@ -641,14 +727,18 @@ struct rgrg_engine {
     ensure_roi_ws(P_total);
     const float scale = exp2f(roundf(log2f(static_cast<float>(f) / static_cast<float>(S))));  // poolers.py _infer_scale
     if (P_total > 0) {
-      det::roi_align_kernel<<<dim3(TOPK, B), 256, 0, st>>>(feats.as<bf16>(), prop_boxes.as<float>(), prop_count.as<int>(),
-                                                          roi_off.as<int>(), pooled.as<bf16>(), f, 2048, scale);
-      KERNEL_CHECK();
-      ++launches;
-      gemm(pooled.as<bf16>(), P_total, fc6, store_bf16(f6.as<bf16>(), fc6.bias, 1024, ACT_RELU), st, false);
-      gemm(f6.as<bf16>(), P_total, fc7, store_bf16(f7.as<bf16>(), fc7.bias, 1024, ACT_RELU), st, true);
-      gemm(f7.as<bf16>(), P_total, pred, store_f32(pred_out.as<float>(), pred.bias, 150, ACT_NONE), st, true);
+      {
+        ProfScope ps(this, "roi_align", st);
+        det::roi_align_kernel<<<dim3(TOPK, B), 256, 0, st>>>(feats.as<bf16>(), prop_boxes.as<float>(), prop_count.as<int>(),
+                                                            roi_off.as<int>(), pooled.as<bf16>(), f, 2048, scale);
+        KERNEL_CHECK();
+        ++launches;
+      }
+      gemm("fc6", pooled.as<bf16>(), P_total, fc6, store_bf16(f6.as<bf16>(), fc6.bias, 1024, ACT_RELU), st, false);
+      gemm("fc7", f6.as<bf16>(), P_total, fc7, store_bf16(f7.as<bf16>(), fc7.bias, 1024, ACT_RELU), st, true);
+      gemm("box_predictor", f7.as<bf16>(), P_total, pred, store_f32(pred_out.as<float>(), pred.bias, 150, ACT_NONE), st, true);
     }
+    ProfScope ps_tail(this, "region_tail", st);
     det::RoiTailOut to{detected.as<uint8_t>(), top_idx.as<int>(), top_scores.as<float>(), top_boxes.as<float>()};
     det::roi_tail_kernel<<<B, 256, 0, st>>>(pred_out.as<float>(), 150, pred_out.as<float>() + 30, 150, prop_boxes.as<float>(),
                                             prop_count.as<int>(), roi_off.as<int>(), to, S);
@@ -710,10 +800,10 @@ struct rgrg_engine {
 
   // language_model.py:284 (once instead of every step) + :140-147 for all 24 layers in one GEMM
   void lm_prologue(const bf16* feats_bf16, int R, int beams, cudaStream_t st) {
-    gemm(feats_bf16, R, fst0, store_bf16(a1.as<bf16>(), fst0.bias, DM, ACT_RELU), st, true);
-    gemm(a1.as<bf16>(), R, fst2, store_bf16(img.as<bf16>(), fst2.bias, DM, ACT_NONE), st, true);
+    gemm("lm_prologue", feats_bf16, R, fst0, store_bf16(a1.as<bf16>(), fst0.bias, DM, ACT_RELU), st, true);
+    gemm("lm_prologue", a1.as<bf16>(), R, fst2, store_bf16(img.as<bf16>(), fst2.bias, DM, ACT_NONE), st, true);
     EpiImageKv e{ukv.bias, kv_geom(), beams};
-    gemm(img.as<bf16>(), R, ukv, e, st, true);
+    gemm("lm_image_kv", img.as<bf16>(), R, ukv, e, st, true);
   }
 
   // one decode step for `rows` rows; every kernel reads the step index from device memory.
@@ -721,36 +811,53 @@ struct rgrg_engine {
   int decode_step(int rows, const dec::GreedyState& g, float* logits_out, cudaStream_t st) {
     const int before = static_cast<int>(launches);
     const int* sp = step.as<int>();
-    dec::embed_kernel<<<rows, 256, 0, st>>>(wte_f32, g.ids, g.ids_ld, sp, h.as<float>());
-    KERNEL_CHECK();
-    ++launches;
+    {
+      ProfScope ps(this, "embed", st);
+      dec::embed_kernel<<<rows, 256, 0, st>>>(wte_f32, g.ids, g.ids_ld, sp, h.as<float>());
+      KERNEL_CHECK();
+      ++launches;
+    }
     const int ln_grid = ceil_div(rows, 8);
     for (int l = 0; l < NLAYER; ++l) {
       const LayerW& L = layers[l];
-      dec::layernorm_kernel<<<ln_grid, 256, 0, st>>>(h.as<float>(), L.ln1_g, L.ln1_b, x.as<bf16>(), rows);
-      KERNEL_CHECK();
+      {
+        ProfScope ps(this, "layernorm", st);
+        dec::layernorm_kernel<<<ln_grid, 256, 0, st>>>(h.as<float>(), L.ln1_g, L.ln1_b, x.as<bf16>(), rows);
+        KERNEL_CHECK();
+      }
       EpiQkvAppend eq{q.as<bf16>(), L.attn.bias, kv_geom(), l, sp};
-      gemm(x.as<bf16>(), rows, L.attn, eq, st, true);
-      dec::attention_kernel<<<ceil_div(rows * 16, 4), 128, 0, st>>>(q.as<bf16>(), kv_geom(), l, sp, attn_o.as<bf16>(), rows);
-      KERNEL_CHECK();
-      gemm(attn_o.as<bf16>(), rows, L.proj, store_f32(h.as<float>(), L.proj.bias, DM, ACT_NONE, h.as<float>()), st, true);
-      dec::layernorm_kernel<<<ln_grid, 256, 0, st>>>(h.as<float>(), L.ln2_g, L.ln2_b, x.as<bf16>(), rows);
-      KERNEL_CHECK();
-      gemm(x.as<bf16>(), rows, L.fc, store_bf16(mlp_mid.as<bf16>(), L.fc.bias, 4 * DM, ACT_GELU_NEW), st, true);
-      gemm(mlp_mid.as<bf16>(), rows, L.mproj, store_f32(h.as<float>(), L.mproj.bias, DM, ACT_NONE, h.as<float>()), st, true);
+      gemm("c_attn", x.as<bf16>(), rows, L.attn, eq, st, true);
+      {
+        ProfScope ps(this, "attention", st);
+        dec::attention_kernel<<<ceil_div(rows * 16, 4), 128, 0, st>>>(q.as<bf16>(), kv_geom(), l, sp, attn_o.as<bf16>(), rows);
+        KERNEL_CHECK();
+      }
+      gemm("attn_c_proj", attn_o.as<bf16>(), rows, L.proj, store_f32(h.as<float>(), L.proj.bias, DM, ACT_NONE, h.as<float>()), st, true);
+      {
+        ProfScope ps(this, "layernorm", st);
+        dec::layernorm_kernel<<<ln_grid, 256, 0, st>>>(h.as<float>(), L.ln2_g, L.ln2_b, x.as<bf16>(), rows);
+        KERNEL_CHECK();
+      }
+      gemm("mlp_c_fc", x.as<bf16>(), rows, L.fc, store_bf16(mlp_mid.as<bf16>(), L.fc.bias, 4 * DM, ACT_GELU_NEW), st, true);
+      gemm("mlp_c_proj", mlp_mid.as<bf16>(), rows, L.mproj, store_f32(h.as<float>(), L.mproj.bias, DM, ACT_NONE, h.as<float>()), st, true);
       launches += 3;
     }
-    dec::layernorm_kernel<<<ln_grid, 256, 0, st>>>(h.as<float>(), lnf_g, lnf_b, x.as<bf16>(), rows);
-    KERNEL_CHECK();
-    ++launches;
+    {
+      ProfScope ps(this, "layernorm", st);
+      dec::layernorm_kernel<<<ln_grid, 256, 0, st>>>(h.as<float>(), lnf_g, lnf_b, x.as<bf16>(), rows);
+      KERNEL_CHECK();
+      ++launches;
+    }
     if (logits_out || opt_gemm_impl == 2) {
       float* dst = logits_out ? logits_out : logits_tmp.as<float>();
-      gemm(x.as<bf16>(), rows, lm_head, store_f32(dst, nullptr, VOCAB, ACT_NONE), st, true);
+      gemm("lm_head", x.as<bf16>(), rows, lm_head, store_f32(dst, nullptr, VOCAB, ACT_NONE), st, true);
+      ProfScope ps(this, "greedy_update", st);
       dec::greedy_update_kernel<<<1, 1024, 0, st>>>(nullptr, nullptr, 0, dst, g, rows);
     } else {
       const int n_tiles = ceil_div(VOCAB, 128);
       EpiArgmaxPartial ea{part_val.as<float>(), part_idx.as<int>(), n_tiles};
-      gemm(x.as<bf16>(), rows, lm_head, ea, st, true, 128);
+      gemm("lm_head", x.as<bf16>(), rows, lm_head, ea, st, true, 128);
+      ProfScope ps(this, "greedy_update", st);
       dec::greedy_update_kernel<<<1, 1024, 0, st>>>(part_val.as<float>(), part_idx.as<int>(), n_tiles, nullptr, g, rows);
     }
     KERNEL_CHECK();
@@ -778,7 +885,7 @@ struct rgrg_engine {
     const int graph_key = R * 4096 + max_length;
     // step 0 always runs eagerly (it also makes sure every kernel is loaded and configured before a capture)
     decode_step(R, g, nullptr, st);
-    if (opt_cuda_graph && steps > 1) {
+    if (opt_cuda_graph && !prof_on && steps > 1) {
       auto it = step_graphs.find(graph_key);
       if (it == step_graphs.end()) {
         cudaGraph_t graph;
@@ -839,6 +946,20 @@ struct rgrg_engine {
   }
 };
 
+ProfScope::ProfScope(rgrg_engine* e_, const char* tag, cudaStream_t st_) : e(e_), st(st_), rec(-1) {
+  if (!e->prof_on) return;
+  rgrg_engine::ProfRec r;
+  r.cat = e->prof_cat(tag);
+  r.a = e->prof_event();
+  r.b = e->prof_event();
+  cudaEventRecord(r.a, st);
+  rec = static_cast<int>(e->prof_recs.size());
+  e->prof_recs.push_back(r);
+}
+ProfScope::~ProfScope() {
+  if (rec >= 0) cudaEventRecord(e->prof_recs[rec].b, st);
+}
+
 // ====================================================================================================================
 // C ABI
 // ====================================================================================================================
@@ -893,8 +1014,22 @@ const char* rgrg_last_error(const rgrg_engine_t* e) { return e ? e->err.c_str() 
 
 int64_t rgrg_kernel_launches(const rgrg_engine_t* e) { return e->launches; }
 
+int rgrg_profile_read(rgrg_engine_t* e, char* buf, size_t buflen) {
+  RGRG_TRY(e, {
+    const std::string r = e->prof_report();
+    if (r.size() + 1 > buflen) throw std::runtime_error("profile buffer too small");
+    memcpy(buf, r.c_str(), r.size() + 1);
+    e->prof_reset();
+  });
+}
+
 int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   const std::string k(key);
+  if (k == "profile") {
+    e->prof_on = value != 0;
+    e->prof_reset();
+    return 0;
+  }
   if (k == "implicit_conv") e->opt_implicit_conv = value;
   else if (k == "cuda_graph") e->opt_cuda_graph = value;
   else if (k == "gemm_impl") e->opt_gemm_impl = value;
@@ -944,7 +1079,7 @@ int rgrg_detect(rgrg_engine_t* e, const float* images, int images_on_host, int B
                 int32_t* out_top_idx, int32_t* out_num_proposals, int* out_R, void* stream) {
   RGRG_TRY(e, {
     check_ready(e);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t st = e->enter(stream);
     const float* img = stage_images(e, images, images_on_host, B, S, st);
     const int R = e->run_detect(img, B, S, st);
     if (out_R) *out_R = R;
@@ -961,7 +1096,7 @@ int rgrg_generate(rgrg_engine_t* e, const float* images, int images_on_host, int
     if (num_beams != 1) throw std::runtime_error("beam search is not available in this build (num_beams must be 1)");
     if (max_length < 2 || max_length > 1024) throw std::runtime_error("max_length must be in [2, 1024]");
     (void)early_stopping;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t st = e->enter(stream);
     const float* img = stage_images(e, images, images_on_host, B, S, st);
     const int R = e->run_detect(img, B, S, st);
     *out_R = R;
@@ -995,7 +1130,7 @@ int rgrg_lm_generate(rgrg_engine_t* e, const float* feats, int feats_on_host, in
     if (max_length < 2 || max_length > 1024) throw std::runtime_error("max_length must be in [2, 1024]");
     if (R <= 0) throw std::runtime_error("R must be positive");
     (void)early_stopping;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t st = e->enter(stream);
     const bf16* f = stage_feats(e, feats, feats_on_host, R, st);
     const int width = e->run_greedy(f, R, max_length, out_ids, st);
     if (out_width) *out_width = width;
@@ -1006,7 +1141,7 @@ int rgrg_lm_forced_logits(rgrg_engine_t* e, const float* feats_dev, int R, const
                           float* out_logits_dev, void* stream) {
   RGRG_TRY(e, {
     check_ready(e);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t st = e->enter(stream);
     const bf16* f = stage_feats(e, feats_dev, 0, R, st);
     e->ensure_decoder_ws(R, n_tokens + 1);
     e->lm_prologue(f, R, 1, st);
@@ -1030,7 +1165,7 @@ int rgrg_rpn_filter(rgrg_engine_t* e, const float* objectness_dev, const float* 
                     int32_t* topk_idx_dev, int32_t* keep_rank_dev, void* stream) {
   RGRG_TRY(e, {
     check_ready(e);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t st = e->enter(stream);
     const long long N = static_cast<long long>(feat) * feat * det::NUM_ANCHORS;
     det::RpnIn in{};
     in.obj = objectness_dev;
@@ -1049,7 +1184,7 @@ int rgrg_rpn_filter(rgrg_engine_t* e, const float* objectness_dev, const float* 
 int rgrg_roi_align(rgrg_engine_t* e, const void* feats_bf16_dev, const float* boxes_dev, const int32_t* count_dev, int B,
                    int feat, int C, int image_size, void* out_bf16_dev, void* stream) {
   RGRG_TRY(e, {
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t st = e->enter(stream);
     if (C % 8) throw std::runtime_error("C must be a multiple of 8");
     e->roi_off.ensure(static_cast<size_t>(B + 1) * 4);
     det::roi_offsets_kernel<<<1, 32, 0, st>>>(count_dev, e->roi_off.as<int>(), B);
@@ -1066,7 +1201,7 @@ int rgrg_roi_tail(rgrg_engine_t* e, const float* class_logits_dev, const float* 
                   const int32_t* count_dev, int B, int image_size, uint8_t* detected_dev, int32_t* top_idx_dev,
                   float* scores_dev, float* top_boxes_dev, void* stream) {
   RGRG_TRY(e, {
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t st = e->enter(stream);
     e->roi_off.ensure(static_cast<size_t>(B + 1) * 4);
     det::roi_offsets_kernel<<<1, 32, 0, st>>>(count_dev, e->roi_off.as<int>(), B);
     det::RoiTailOut to{detected_dev, top_idx_dev, scores_dev, top_boxes_dev};
@@ -1081,7 +1216,7 @@ int rgrg_roi_tail(rgrg_engine_t* e, const float* class_logits_dev, const float* 
 int rgrg_gemm_bf16(rgrg_engine_t* e, const void* A_dev, const void* W_dev, const float* bias_dev, int M, int N, int K, int act,
                    int impl, float* out_dev, void* stream) {
   RGRG_TRY(e, {
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t st = e->enter(stream);
     Linear L;
     L.w = static_cast<bf16*>(const_cast<void*>(W_dev));
     L.bias = const_cast<float*>(bias_dev);
@@ -1092,7 +1227,7 @@ int rgrg_gemm_bf16(rgrg_engine_t* e, const void* A_dev, const void* W_dev, const
     e->opt_gemm_impl = impl == 2 ? 2 : 0;
     try {
       if (impl != 2) L.make_maps();
-      e->gemm(static_cast<const bf16*>(A_dev), M, L, ep, st, true, impl == 0 ? 128 : (impl == 1 ? 64 : 0));
+      e->gemm("test_gemm", static_cast<const bf16*>(A_dev), M, L, ep, st, true, impl == 0 ? 128 : (impl == 1 ? 64 : 0));
     } catch (...) {
       e->opt_gemm_impl = saved;
       throw;
@@ -1105,7 +1240,7 @@ int rgrg_gemm_bf16(rgrg_engine_t* e, const void* A_dev, const void* W_dev, const
 int rgrg_conv3x3_bf16(rgrg_engine_t* e, const void* in_dev, const void* w_dev, const float* bias_dev, int B, int H, int W,
                       int Cin, int Cout, int relu, int implicit, float* out_dev, void* stream) {
   RGRG_TRY(e, {
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t st = e->enter(stream);
     Linear L;
     L.w = static_cast<bf16*>(const_cast<void*>(w_dev));
     L.bias = const_cast<float*>(bias_dev);
@@ -1116,7 +1251,7 @@ int rgrg_conv3x3_bf16(rgrg_engine_t* e, const void* in_dev, const void* w_dev, c
     const int saved = e->opt_implicit_conv;
     e->opt_implicit_conv = implicit;
     try {
-      e->conv3x3(static_cast<const bf16*>(in_dev), B, H, W, Cin, 1, L, ep, st);
+      e->conv3x3("test_conv", static_cast<const bf16*>(in_dev), B, H, W, Cin, 1, L, ep, st);
     } catch (...) {
       e->opt_implicit_conv = saved;
       throw;
@@ -1129,7 +1264,7 @@ int rgrg_conv3x3_bf16(rgrg_engine_t* e, const void* in_dev, const void* w_dev, c
 int rgrg_backbone(rgrg_engine_t* e, const float* images_dev, int B, int S, void* out_feats_bf16_dev, void* stream) {
   RGRG_TRY(e, {
     check_ready(e);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaStream_t st = e->enter(stream);
     e->ensure_detector_ws(B, S);
     e->run_backbone(images_dev, B, S, static_cast<bf16*>(out_feats_bf16_dev), st);
     CUDA_CHECK(cudaStreamSynchronize(st));

@@ -57,6 +57,16 @@ class Engine:
     def set_option(self, key: str, value: int):
         self._check(self._lib.rgrg_set_option(self._h, key.encode(), int(value)))
 
+    def profile_read(self):
+        """-> {category: (total_ms, launches)} since set_option("profile", 1)."""
+        buf = C.create_string_buffer(1 << 16)
+        self._check(self._lib.rgrg_profile_read(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, n = line.split()
+            out[name] = (float(ms), int(n))
+        return out
+
     @property
     def kernel_launches(self) -> int:
         return int(self._lib.rgrg_kernel_launches(self._h))
