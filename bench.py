@@ -103,6 +103,58 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def log(msg):
+    print("[bench %s] %s" % (time.strftime("%H:%M:%S"), msg), file=sys.stderr, flush=True)
+
+
+def timed_oracle_generate(sd, img, T, decode_budget_s=25.0):
+    """The reference's CPU algorithm (oracle port) on one batch, with a BOUNDED decode: the greedy loop
+    (language_model.py:609-652 as restated by rgrg_oracle.lm_forward) is stepped until T-1 steps are done or the
+    budget is spent; the remaining steps are extrapolated with a least-squares line through the measured per-step
+    times (the reference regrows the KV cache with torch.cat every step, so step time grows linearly with t).
+    Returns (seconds for the whole generate(), description)."""
+    import numpy as np
+    import torch
+
+    import rgrg_oracle as O
+
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        det = O.detect(sd, img)
+        selected, feats, _ = O.region_selection(sd, det["top_region_features"], det["class_detected"])
+    t_det = time.perf_counter() - t0
+    R = int(feats.shape[0])
+    step_times = []
+    if R > 0:
+        ids = torch.full((R, 1), O.BOS, dtype=torch.int64)
+        mask = torch.ones(R, 1, dtype=torch.int64)
+        past = None
+        with torch.no_grad():
+            for t in range(T - 1):
+                ts = time.perf_counter()
+                inp = ids if past is None else ids[:, -1:]
+                pos = mask.cumsum(-1) - 1
+                pos = pos if past is None else pos[:, -1:]
+                logits, past = O.lm_forward(sd, inp, feats, past, pos, mask)
+                nxt = torch.argmax(logits[:, -1, :], dim=-1)
+                ids = torch.cat([ids, nxt[:, None]], dim=-1)
+                mask = torch.cat([mask, mask.new_ones(R, 1)], dim=-1)
+                step_times.append(time.perf_counter() - ts)
+                if sum(step_times) > decode_budget_s and len(step_times) >= 4:
+                    break
+    n = len(step_times)
+    t_dec = sum(step_times)
+    extrap = ""
+    if 0 < n < T - 1:
+        xs = np.arange(n, dtype=np.float64)
+        a, b = np.polyfit(xs[1:], np.array(step_times[1:]), 1) if n > 2 else (0.0, step_times[-1])
+        rest = np.arange(n, T - 1, dtype=np.float64)
+        t_dec += float(np.sum(np.maximum(a * rest + b, step_times[-1])))
+        extrap = ", %d of %d decode steps measured, rest extrapolated linearly" % (n, T - 1)
+    desc = "%d image(s), R=%d rows, detector %.1f s + decoder %.1f s%s" % (img.shape[0], R, t_det, t_dec, extrap)
+    return t_det + t_dec, R, desc
+
+
 def flops_per_image(S, P, R, T):
     """SURVEY.md §8(d) algorithmic work (MACs x 2)."""
     s2 = (S / 512.0) ** 2
@@ -148,27 +200,23 @@ def run_reference_arm(args, rank, world):
 
     from rgrg_b200 import synth
 
-    torch.set_num_threads(os.cpu_count() or 1)
     sd = synth.make_state_dict(0)
     T = args.max_length
     times = []
-    R_seen = P_seen = 0
+    desc = ""
+    # every step is a bounded sample (1 image; decode time-boxed) so that W + K steps end within a few minutes
+    budget = max(4.0, min(25.0, 200.0 / max(1, args.warmup + args.steps) - 4.0))
     for step in range(args.warmup + args.steps):
         img = synth.synthetic_images(1, args.image_size, seed=2000 + step)
-        t0 = time.perf_counter()
-        with torch.no_grad():
-            detail = {}
-            out = O.generate(sd, img, max_length=T, detail=detail)
-        dt = time.perf_counter() - t0
+        dt, R_seen, desc = timed_oracle_generate(sd, img, T, decode_budget_s=budget)
+        log("reference step %d: %.1f s (%s)" % (step, dt, desc))
         if step >= args.warmup:
             times.append(dt)
-        R_seen = 0 if out == -1 else int(out[0].shape[0])
-        P_seen = int(sum(p.shape[0] for p in detail["proposals"]))
     total = sum(times)
     value = len(times) * 1.0 / total
     cores = torch.get_num_threads()
-    sample = "1 image / step, %dx%d, greedy max_length=%d, fp32, R=%d rows, P=%d proposals (same per-image work as the GPU arm)" % (
-        args.image_size, args.image_size, T, R_seen, P_seen)
+    sample = "1 image / step, %dx%d, greedy max_length=%d, fp32 oracle port of the reference algorithm; last step: %s" % (
+        args.image_size, args.image_size, T, desc)
     line = {
         "impl": "reference", "metric": "reports_per_sec", "value": value, "unit": "reports/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
@@ -199,16 +247,11 @@ def cpu_baseline(args, sd):
 
     from rgrg_b200 import synth
 
-    torch.set_num_threads(os.cpu_count() or 1)
     img = synth.synthetic_images(1, args.image_size, seed=2000)
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        out = O.generate(sd, img, max_length=args.max_length)
-    dt = time.perf_counter() - t0
-    R = 0 if out == -1 else int(out[0].shape[0])
+    dt, R, desc = timed_oracle_generate(sd, img, args.max_length, decode_budget_s=20.0)
     return {"value": 1.0 / dt, "unit": "reports/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "1 image, %dx%d, greedy max_length=%d, R=%d rows, fp32 oracle port of the reference algorithm, %.1f s"
-                      % (args.image_size, args.image_size, args.max_length, R, dt)}
+            "sample": "%dx%d, greedy max_length=%d, fp32 oracle port of the reference algorithm: %s"
+                      % (args.image_size, args.image_size, args.max_length, desc)}
 
 
 def main():
@@ -250,6 +293,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    log("rank %d/%d: building synthetic checkpoint" % (rank, world))
     sd = synth.make_state_dict(0) if rank == 0 else None
     if world > 1:
         dist.barrier()
@@ -259,6 +303,7 @@ def main():
     model.load_state_dict(sd)
     model.to(dev)
     model.eval()
+    log("loading weights into the engine")
     eng = model._engine()
 
     B, T, S = args.batch, args.max_length, args.image_size
@@ -291,12 +336,14 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
+    log("warm-up x%d" % args.warmup)
     # ---- warm-up
     last = None
     for i in range(args.warmup):
         last = step_device(i)
     sync_all()
 
+    log("timed region (device-resident inputs) x%d" % args.steps)
     # ---- timed: device-resident inputs
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -318,6 +365,7 @@ def main():
     ms_max = float(t_ms.item())
     value = world * B * args.steps / (ms_max / 1e3)
 
+    log("%.1f reports/s; timed region (e2e, host buffers)" % value)
     # ---- timed: end to end through the reference-facing API, host buffers
     for i in range(min(args.warmup, 2)):
         step_e2e(i)
@@ -335,6 +383,7 @@ def main():
     d2h = R * T * 4 + 2 * B * 29 + B * 29 * 16 + B * 29 * 4 + R * T * 8  # engine outputs + the caller's ids.cpu()
     e2e = {"value": e2e_value, "unit": "reports/s", "h2d_bytes_per_step": B * S * S * 4, "d2h_bytes_per_step": d2h}
 
+    log("e2e %.1f reports/s; profiled step" % e2e_value)
     # ---- roofline: one profiled step (CUDA events around every kernel category on the launch stream)
     roofline, breakdown = None, None
     if rank == 0:
@@ -377,6 +426,7 @@ def main():
             "kernel_breakdown": breakdown,
         }
         if not args.no_cpu_baseline and world == 1:
+            log("cpu baseline (bounded sample)")
             line["cpu_baseline"] = cpu_baseline(args, sd)
         print(json.dumps(line), flush=True)
     if world > 1:

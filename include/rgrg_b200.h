@@ -59,6 +59,7 @@ RGRG_API int rgrg_finalize_weights(rgrg_engine_t* e);
 /* ---- the hot path ---------------------------------------------------------------------------------------------- */
 
 /* replaces: ReportGenerationModel.generate(images, max_length, num_beams=1) (report_generation_model.py:212-276).
+ * num_beams > 1 runs beam search (language_model.py:529-607) with BeamSearchScorer(length_penalty=1, keep 1).
  * images: fp32 [B,1,S,S] (host or device).  Host outputs:
  *   out_ids      int32 [B*29, max_length]  rows 0..R-1 valid (image-major, region-minor order of selected regions),
  *                                          column 0 = BOS, finished rows padded with 50256
@@ -88,6 +89,12 @@ RGRG_API int rgrg_detect(rgrg_engine_t* e, const float* images, int images_on_ho
 RGRG_API int rgrg_lm_forced_logits(rgrg_engine_t* e, const float* feats_dev, int R, const int32_t* forced_ids_dev,
                           int n_tokens, float* out_logits_dev, void* stream);
 
+/* beam-search bookkeeping only (language_model.py:556-605 + BeamSearchScorer.process / finalize) driven by given logits:
+ * logits_steps dev fp32 [n_steps, sentences*num_beams, 50257] (row b of step t is what beam slot b sees at step t);
+ * out_ids host int32 [sentences, max_length]; stops early when every sentence is done, like the reference loop. */
+RGRG_API int rgrg_beam_bookkeeping(rgrg_engine_t* e, const float* logits_steps_dev, int n_steps, int sentences, int num_beams,
+                          int max_length, int early_stopping, int32_t* out_ids, int* out_width, void* stream);
+
 /* RPN filter_proposals (torchvision rpn.py:242-297) on given fp32 head outputs.
  * objectness dev [B,N]; deltas dev [B,N,4] (or NULL when decoded_boxes dev [B,N,4] is given); N = feat*feat*160.
  * outputs (dev): boxes [B,1000,4], scores [B,1000], count [B], topk_idx [B,1000] (opt), keep_rank [B,1000] (opt) */
@@ -107,7 +114,8 @@ RGRG_API int rgrg_roi_tail(rgrg_engine_t* e, const float* class_logits_dev, cons
                   int32_t* top_idx_dev, float* scores_dev, float* top_boxes_dev, void* stream);
 
 /* D[M,N] (fp32 dev) = A[M,K] (bf16 dev) * W[N,K]^T (bf16 dev) + bias[N] (fp32 dev or NULL).
- * impl: 0 = tcgen05 BN=128, 1 = tcgen05 BN=64, 2 = CUDA-core cross-check.  act: 0 none, 1 relu, 2 gelu_new. */
+ * impl: 0 / 1 / 3 / 4 = tcgen05 with N tile 128 / 64 / 192 / 256, 5 = tcgen05 with the engine's own tile choice,
+ *       2 = CUDA-core cross-check.  act: 0 none, 1 relu, 2 gelu_new. */
 RGRG_API int rgrg_gemm_bf16(rgrg_engine_t* e, const void* A_dev, const void* W_dev, const float* bias_dev, int M, int N, int K,
                    int act, int impl, float* out_dev, void* stream);
 

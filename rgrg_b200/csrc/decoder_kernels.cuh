@@ -13,6 +13,15 @@ constexpr int HD = 64;
 constexpr int VOCAB = 50257;
 constexpr int EOS_ID = 50256;  // bos == eos == pad (language_model.py:200-202)
 
+// order-preserving float <-> uint32 key (ascending)
+__device__ __forceinline__ unsigned float_key_dec(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_key_dec(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
 // K15  h[r] = wte[token] + wte[position]   — positions are embedded through wte, not wpe (language_model.py:307)
 // token of row r at step t = ids[r, t]; position = t.
 __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ wte, const int* __restrict__ ids, int ids_ld,
@@ -68,8 +77,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // scores = q.K^T / 8 over slots [0, t+2) (slot 0 = image key), softmax in fp32, out = P.V.  The causal / padding
 // masks are all-pass in generate().  One warp per (row, head); K and V rows are read as contiguous 128-byte lines:
 // lane l holds dims (l%8)*8..+8 of key 4*i + l/8.
+// Beam search: `anc` (optional) maps (row, slot) to the beam of the same sentence whose physical cache row holds that
+// slot, so the reference's per-step index_select of the whole cache (language_model.py:492-496) becomes a table lookup.
 __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__ q, KvGeom kv, int layer,
-                                                        const int* __restrict__ step_ptr, bf16* __restrict__ out, int rows) {
+                                                        const int* __restrict__ step_ptr, bf16* __restrict__ out, int rows,
+                                                        const unsigned char* __restrict__ anc, int anc_ld, int nb) {
   const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (gw >= rows * HEADS) return;
@@ -81,6 +93,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
   unpack8(*reinterpret_cast<const uint4*>(q + static_cast<size_t>(row) * D + head * HD + dseg * 8), qv);
   const bf16* Kp = kv.cache + kv.offset(layer, 0, row, head, 0);
   const bf16* Vp = kv.cache + kv.offset(layer, 1, row, head, 0);
+  const int sent_row0 = anc ? (row / nb) * nb : 0;
+  const unsigned char* arow = anc ? anc + static_cast<size_t>(row) * anc_ld : nullptr;
 
   // online softmax: each of the 4 key subgroups keeps its own running (max, denominator, accumulator); K and V of a
   // key are fetched together so both 16-byte loads are in flight before the dependent math
@@ -95,8 +109,15 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
     const bool ok = key < L;
     uint4 kraw = make_uint4(0, 0, 0, 0), vraw = make_uint4(0, 0, 0, 0);
     if (ok) {
-      kraw = *reinterpret_cast<const uint4*>(Kp + static_cast<size_t>(key) * HD + dseg * 8);
-      vraw = *reinterpret_cast<const uint4*>(Vp + static_cast<size_t>(key) * HD + dseg * 8);
+      const bf16* kp = Kp;
+      const bf16* vp = Vp;
+      if (anc) {
+        const int prow = sent_row0 + arow[key];
+        kp = kv.cache + kv.offset(layer, 0, prow, head, 0);
+        vp = kv.cache + kv.offset(layer, 1, prow, head, 0);
+      }
+      kraw = *reinterpret_cast<const uint4*>(kp + static_cast<size_t>(key) * HD + dseg * 8);
+      vraw = *reinterpret_cast<const uint4*>(vp + static_cast<size_t>(key) * HD + dseg * 8);
     }
     float kf[8], vf[8];
     unpack8(kraw, kf);
@@ -142,28 +163,27 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
 
 // K22/K23  arg-max over the vocabulary + greedy bookkeeping (language_model.py:629-650).  One CTA.
 //   next = argmax(logits) (lowest index on ties); finished rows emit pad; ids[:, t+1] = next; a row finishes when it
-//   emits EOS; unfinished_count[t] lets the host stop early without a per-step sync; finally step += 1.
+//   emits EOS; unfinished_count[t] lets the host stop early without a per-step sync; the last CTA does step += 1.
 // Source of the arg-max: tile partials of the fused lm_head epilogue (part_*), or a full fp32 logits matrix.
 struct GreedyState {
   int* ids;          // [rows, ids_ld]
   int ids_ld;
   int* unfinished;   // [rows] 1 = still generating
-  int* unfinished_count;  // [max_steps]
+  int* unfinished_count;  // [max_steps], zeroed by greedy_init_kernel
+  int* ticket;       // CTA arrival counter of greedy_update_kernel
   int* step_ptr;
   const int* forced; // optional [rows, ids_ld]: teacher forcing — ids[:, t+1] = forced[:, t+1], arg-max is only recorded
   int* argmax_out;   // optional [max_steps, rows] raw arg-max per step (tests)
 };
 
-__global__ void __launch_bounds__(1024) greedy_update_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx,
-                                                             int n_tiles, const float* __restrict__ logits /*or null*/,
-                                                             GreedyState g, int rows) {
-  __shared__ int s_cnt;
-  if (threadIdx.x == 0) s_cnt = 0;
-  __syncthreads();
+__global__ void __launch_bounds__(256) greedy_update_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx,
+                                                            int n_tiles, const float* __restrict__ logits /*or null*/,
+                                                            GreedyState g, int rows) {
+  // one warp per row, 8 rows per CTA; the last CTA to finish publishes step + 1 (all CTAs read the step first)
   const int t = *g.step_ptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int local_unfinished = 0;
-  for (int r = warp; r < rows; r += 32) {
+  const int r = blockIdx.x * 8 + warp;
+  if (r < rows) {
     float best = -INFINITY;
     int idx = 0x7fffffff;
     if (logits) {
@@ -198,25 +218,270 @@ __global__ void __launch_bounds__(1024) greedy_update_kernel(const float* __rest
         g.unfinished[r] = unf;
       }
       if (in_range) g.ids[static_cast<size_t>(r) * g.ids_ld + t + 1] = nxt;
-      local_unfinished += unf;
+      if (unf) atomicAdd(&g.unfinished_count[t], 1);
     }
   }
-  if (lane == 0 && local_unfinished) atomicAdd(&s_cnt, local_unfinished);
   __syncthreads();
   if (threadIdx.x == 0) {
-    g.unfinished_count[t] = s_cnt;
-    *g.step_ptr = t + 1;
+    __threadfence();
+    const int ticket = atomicAdd(g.ticket, 1);
+    if (ticket == static_cast<int>(gridDim.x) - 1) {
+      *g.ticket = 0;
+      *g.step_ptr = t + 1;
+    }
   }
 }
 
 // start of a generate() call: ids[:, 0] = BOS, unfinished = 1, step = 0
 __global__ void greedy_init_kernel(GreedyState g, int rows) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < g.ids_ld) g.unfinished_count[r] = 0;
+  if (r == 0) *g.ticket = 0;
   if (r < rows) {
     g.ids[static_cast<size_t>(r) * g.ids_ld] = g.forced ? g.forced[static_cast<size_t>(r) * g.ids_ld] : EOS_ID;
     g.unfinished[r] = 1;
   }
   if (r == 0) *g.step_ptr = 0;
+}
+
+}  // namespace dec
+}  // namespace rgrg
+
+// =====================================================================================================================
+// Beam search (language_model.py:529-607 + transformers==4.19.2 BeamSearchScorer, restated in oracle/beam_scorer.py)
+// Rows = sentences x beams.  All bookkeeping stays on the device; only finalize() runs on the host, once.
+// =====================================================================================================================
+namespace rgrg {
+namespace dec {
+
+constexpr int MAX_BEAMS = 8;
+
+struct BeamState {
+  int nb;             // beams per sentence
+  int ids_ld;         // max_length
+  int* ids[2];        // [rows, ids_ld] double-buffered token matrix (reordered every step)
+  unsigned char* anc[2];  // [rows, slots] physical beam (within the sentence) holding each cache slot of a row
+  int slots;
+  float* beam_scores; // [sentences, nb]
+  float* cand_score;  // [sentences, 2*nb]  top-2nb candidates of the step, sorted descending
+  int* cand_token;    // [sentences, 2*nb]
+  int* cand_beam;     // [sentences, 2*nb]  beam index within the sentence
+  // finished hypotheses (BeamHypotheses): at most nb kept per sentence
+  float* hyp_score;   // [sentences, nb]
+  int* hyp_len;       // [sentences, nb]
+  int* hyp_tok;       // [sentences, nb, ids_ld]
+  int* hyp_count;     // [sentences]
+  float* worst;       // [sentences]
+  int* done;          // [sentences]
+  int* not_done_count;  // [max_steps]
+  int* step_ptr;
+  int early_stopping;
+};
+
+__global__ void beam_init_kernel(BeamState s, int sentences) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int rows = sentences * s.nb;
+  if (i < rows) {
+    s.ids[0][static_cast<size_t>(i) * s.ids_ld] = EOS_ID;  // BOS == EOS (language_model.py:200-202)
+    for (int k = 0; k < s.slots; ++k) s.anc[0][static_cast<size_t>(i) * s.slots + k] = static_cast<unsigned char>(i % s.nb);
+    s.beam_scores[i] = (i % s.nb == 0) ? 0.0f : -1e9f;  // language_model.py:545-547
+  }
+  if (i < sentences) {
+    s.hyp_count[i] = 0;
+    s.worst[i] = 1e9f;
+    s.done[i] = 0;
+  }
+  if (i == 0) *s.step_ptr = 0;
+}
+
+// log_softmax over the vocabulary + beam score, then the 2*nb best of the nb*V candidates of a sentence
+// (language_model.py:556-568).  One CTA per sentence.  Ties -> lowest flat index.
+__global__ void __launch_bounds__(1024) beam_topk_kernel(const float* __restrict__ logits, BeamState s) {
+  __shared__ float s_red[32];
+  __shared__ float s_lse_m[MAX_BEAMS], s_lse_l[MAX_BEAMS];
+  __shared__ unsigned long long s_best[32];
+  __shared__ unsigned long long s_pick;
+  const int sent = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = s.nb;
+  // ---- per beam: max and log-sum-exp
+  for (int b = 0; b < nb; ++b) {
+    const float* l = logits + static_cast<size_t>(sent * nb + b) * VOCAB;
+    float m = -INFINITY;
+    for (int c = tid; c < VOCAB; c += 1024) m = fmaxf(m, l[c]);
+    m = warp_max(m);
+    if (lane == 0) s_red[warp] = m;
+    __syncthreads();
+    m = s_red[lane];
+    m = warp_max(m);
+    __syncthreads();
+    float sum = 0.0f;
+    for (int c = tid; c < VOCAB; c += 1024) sum += expf(l[c] - m);
+    sum = warp_sum(sum);
+    if (lane == 0) s_red[warp] = sum;
+    __syncthreads();
+    sum = warp_sum(s_red[lane]);
+    if (tid == 0) {
+      s_lse_m[b] = m;
+      s_lse_l[b] = logf(sum);
+    }
+    __syncthreads();
+  }
+  // ---- thread-local top-K over its strided share of the nb*V candidates, K = 2*nb
+  const int K = 2 * nb;
+  unsigned long long loc[2 * MAX_BEAMS];
+#pragma unroll
+  for (int i = 0; i < 2 * MAX_BEAMS; ++i) loc[i] = 0ull;
+  const int total = nb * VOCAB;
+  for (int j = tid; j < total; j += 1024) {
+    const int b = j / VOCAB, c = j - b * VOCAB;
+    const float x = logits[static_cast<size_t>(sent * nb + b) * VOCAB + c];
+    const float sc = __fadd_rn(__fsub_rn(__fsub_rn(x, s_lse_m[b]), s_lse_l[b]), s.beam_scores[sent * nb + b]);
+    unsigned long long key = (static_cast<unsigned long long>(float_key_dec(sc)) << 32) | (0xFFFFFFFFu - static_cast<unsigned>(j));
+    if (key > loc[K - 1]) {
+      int p = K - 1;
+      while (p > 0 && loc[p - 1] < key) {
+        loc[p] = loc[p - 1];
+        --p;
+      }
+      loc[p] = key;
+    }
+  }
+  // ---- K rounds of block arg-max over the heads of the per-thread lists
+  int head = 0;
+  for (int r = 0; r < K; ++r) {
+    unsigned long long v = head < K ? loc[head] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ov = __shfl_xor_sync(0xffffffffu, v, o);
+      v = ov > v ? ov : v;
+    }
+    if (lane == 0) s_best[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long w = s_best[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long ov = __shfl_xor_sync(0xffffffffu, w, o);
+        w = ov > w ? ov : w;
+      }
+      if (lane == 0) s_pick = w;
+    }
+    __syncthreads();
+    const unsigned long long pick = s_pick;
+    if (head < K && loc[head] == pick) ++head;  // keys are unique (they embed the flat index)
+    if (tid == 0) {
+      const unsigned j = 0xFFFFFFFFu - static_cast<unsigned>(pick & 0xFFFFFFFFull);
+      s.cand_score[sent * K + r] = float_from_key_dec(static_cast<unsigned>(pick >> 32));
+      s.cand_token[sent * K + r] = static_cast<int>(j % VOCAB);
+      s.cand_beam[sent * K + r] = static_cast<int>(j / VOCAB);
+    }
+    __syncthreads();
+  }
+}
+
+// BeamSearchScorer.process (one thread per sentence) + the reorder of token rows and cache ancestry
+// (language_model.py:570-589).  next token matrix goes to ids[dst], ancestry to anc[dst].
+__global__ void beam_process_kernel(BeamState s, int sentences, int src, int dst) {
+  const int sent = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = *s.step_ptr;       // tokens per row before this step = t + 1 (cur_len in the scorer)
+  const int cur_len = t + 1;
+  const int nb = s.nb, K = 2 * nb;
+  if (sent < sentences) {
+    int next_beam[MAX_BEAMS], next_tok[MAX_BEAMS];
+    float next_score[MAX_BEAMS];
+    if (s.done[sent]) {
+      for (int b = 0; b < nb; ++b) {
+        next_beam[b] = 0;  // the scorer pads finished sentences with (score 0, pad token, beam 0)
+        next_tok[b] = EOS_ID;
+        next_score[b] = 0.0f;
+      }
+    } else {
+      int filled = 0;
+      for (int r = 0; r < K && filled < nb; ++r) {
+        const float sc = s.cand_score[sent * K + r];
+        const int tok = s.cand_token[sent * K + r], bm = s.cand_beam[sent * K + r];
+        if (tok == EOS_ID) {
+          if (r >= nb) continue;
+          // BeamHypotheses.add(input_ids[beam].clone(), sum_logprobs): score = sum_logprobs / len ** 1.0
+          const float hs = sc / static_cast<float>(cur_len);
+          int cnt = s.hyp_count[sent];
+          if (cnt < nb || hs > s.worst[sent]) {
+            int slot = cnt;
+            if (cnt == nb) {
+              // over capacity after the append: drop the lowest (score, insertion index).  hs > worst == min of the held
+              // scores, so the dropped one is always an existing hypothesis; insertion order of the rest is preserved
+              int lo = 0;
+              for (int i = 1; i < nb; ++i)
+                if (s.hyp_score[sent * nb + i] < s.hyp_score[sent * nb + lo]) lo = i;
+              for (int i = lo; i + 1 < nb; ++i) {
+                s.hyp_score[sent * nb + i] = s.hyp_score[sent * nb + i + 1];
+                s.hyp_len[sent * nb + i] = s.hyp_len[sent * nb + i + 1];
+                for (int k = 0; k < s.ids_ld; ++k)
+                  s.hyp_tok[(static_cast<size_t>(sent) * nb + i) * s.ids_ld + k] =
+                      s.hyp_tok[(static_cast<size_t>(sent) * nb + i + 1) * s.ids_ld + k];
+              }
+              slot = nb - 1;
+            }
+            if (slot >= 0) {
+              s.hyp_score[sent * nb + slot] = hs;
+              s.hyp_len[sent * nb + slot] = cur_len;
+              const int* row = s.ids[src] + static_cast<size_t>(sent * nb + bm) * s.ids_ld;
+              for (int k = 0; k < cur_len; ++k) s.hyp_tok[(static_cast<size_t>(sent) * nb + slot) * s.ids_ld + k] = row[k];
+              if (cnt < nb) {
+                s.hyp_count[sent] = cnt + 1;
+                s.worst[sent] = fminf(hs, s.worst[sent]);
+              } else {
+                float w2 = s.hyp_score[sent * nb];
+                for (int i = 1; i < nb; ++i) w2 = fminf(w2, s.hyp_score[sent * nb + i]);
+                s.worst[sent] = w2;
+              }
+            }
+          }
+        } else {
+          next_beam[filled] = bm;
+          next_tok[filled] = tok;
+          next_score[filled] = sc;
+          ++filled;
+        }
+      }
+      // is_done(best_sum_logprobs = max candidate score, cur_len)
+      bool d = false;
+      if (s.hyp_count[sent] >= nb) {
+        if (s.early_stopping) d = true;
+        else d = s.worst[sent] >= s.cand_score[sent * K] / static_cast<float>(cur_len);
+      }
+      if (d) s.done[sent] = 1;
+    }
+    for (int b = 0; b < nb; ++b) {
+      const int row = sent * nb + b;
+      const int from = sent * nb + next_beam[b];
+      s.beam_scores[row] = next_score[b];
+      const int* srow = s.ids[src] + static_cast<size_t>(from) * s.ids_ld;
+      int* drow = s.ids[dst] + static_cast<size_t>(row) * s.ids_ld;
+      for (int k = 0; k < cur_len; ++k) drow[k] = srow[k];
+      if (cur_len < s.ids_ld) drow[cur_len] = next_tok[b];
+      const unsigned char* sa = s.anc[src] + static_cast<size_t>(from) * s.slots;
+      unsigned char* da = s.anc[dst] + static_cast<size_t>(row) * s.slots;
+      for (int k = 0; k <= cur_len && k < s.slots; ++k) da[k] = sa[k];  // slots 0 .. t+1 follow the parent beam
+      for (int k = cur_len + 1; k < s.slots; ++k) da[k] = static_cast<unsigned char>(b);  // future slots: written by the row itself
+    }
+  }
+}
+
+__global__ void beam_step_end_kernel(BeamState s, int sentences) {
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  int c = 0;
+  for (int i = threadIdx.x; i < sentences; i += blockDim.x) c += s.done[i] ? 0 : 1;
+  if (c) atomicAdd(&s_cnt, c);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = *s.step_ptr;
+    s.not_done_count[t] = s_cnt;
+    *s.step_ptr = t + 1;
+  }
 }
 
 }  // namespace dec

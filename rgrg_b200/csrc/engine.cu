@@ -65,10 +65,9 @@ struct Linear {
   bf16* w = nullptr;
   float* bias = nullptr;
   int N = 0, K = 0;
-  CUtensorMap tm128, tm64;
+  CUtensorMap tm[4];  // TMA maps for N-tile widths 64 / 128 / 192 / 256
   void make_maps() {
-    tm128 = tc::make_tmap_2d(w, N, K, 128);
-    tm64 = tc::make_tmap_2d(w, N, K, 64);
+    for (int i = 0; i < 4; ++i) tm[i] = tc::make_tmap_2d(w, N, K, 64 * (i + 1));
   }
 };
 struct LinearF32 {
@@ -193,6 +192,9 @@ struct rgrg_engine {
   int ws_rows = 0, ws_slots = 0;
   DevBuf kv_cache, h, x, q, attn_o, mlp_mid, a1, img, part_val, part_idx, ids, unfinished, unf_count, step, logits_tmp;
   int last_B = 0, last_S = 0, last_P = 0;
+  // beam search: cache-slot ancestry of the current step (null in greedy mode)
+  const unsigned char* beam_anc = nullptr;
+  int beam_slots = 0, beam_nb = 1;
 
   // ---- CUDA graph of one decode step, keyed by row count
   std::map<int, cudaGraphExec_t> step_graphs;
@@ -208,7 +210,8 @@ struct rgrg_engine {
                      &prop_scores, &prop_count, &roi_off, &pooled, &f6, &f7, &pred_out, &detected, &top_idx,
                      &top_scores, &top_boxes, &mean2048, &trf, &s0, &s1, &sel_logits, &selected, &sel_rows, &num_sel,
                      &lm_in, &kv_cache, &h, &x, &q, &attn_o, &mlp_mid, &a1, &img, &part_val, &part_idx, &ids,
-                     &unfinished, &unf_count, &step, &logits_tmp};
+                     &unfinished, &unf_count, &step, &logits_tmp, &b_ids2, &b_anc[0], &b_anc[1], &b_scores, &b_cand_score,
+                     &b_cand_token, &b_cand_beam, &b_hyp_score, &b_hyp_len, &b_hyp_tok, &b_hyp_count, &b_worst, &b_done, &b_not_done};
     for (DevBuf* b : all) b->release();
   }
 
@@ -239,12 +242,7 @@ struct rgrg_engine {
     }
     if (W.K % 64 != 0) throw std::runtime_error("GEMM K must be a multiple of 64");
     const int mt = ceil_div(M, tc::BM);
-    int bn = force_bn;
-    if (!bn) {
-      bn = 128;
-      if (W.N <= 64) bn = 64;
-      else if (mt * ceil_div(W.N, 128) < 148) bn = 64;  // under one wave: halve the tile to occupy more SMs
-    }
+    const int bn = force_bn ? force_bn : pick_bn(mt, W.N);
     tc::GemmShape s{};
     s.M = M;
     s.N = W.N;
@@ -253,9 +251,36 @@ struct rgrg_engine {
     s.n_tiles = ceil_div(W.N, bn);
     s.m_fastest = m_fastest ? 1 : 0;
     CUtensorMap tmA = tc::make_tmap_2d(A, M, W.K, 128);
-    if (bn == 128) tc::launch<128, 6, Epi>(tmA, W.tm128, s, epi, st);
-    else tc::launch<64, 4, Epi>(tmA, W.tm64, s, epi, st);
+    launch_bn(bn, tmA, W, s, epi, st);
     ++launches;
+  }
+
+  // N-tile width: fewest (waves x per-k-block cycles).  Per k-block a 128 x BN tile costs max(2*BN MMA cycles,
+  // (16 KB + BN*128 B) / 128 B/clk of shared-memory operand reads): narrow tiles are smem-bandwidth bound.
+  static int pick_bn(int m_tiles, int N) {
+    int best = 128;
+    long long best_cost = -1;
+    for (int bn = 64; bn <= 256; bn += 64) {
+      const long long tiles = static_cast<long long>(m_tiles) * ceil_div(N, bn);
+      const long long waves = (tiles + tc::num_sms() - 1) / tc::num_sms();
+      const long long cyc = std::max<long long>(2 * bn, (16384 + bn * 128) / 128);
+      const long long cost = waves * (cyc * 16 + 600);  // + fixed per-tile overhead (pipeline fill / drain)
+      if (best_cost < 0 || cost <= best_cost) {
+        best_cost = cost;
+        best = bn;
+      }
+    }
+    return best;
+  }
+  template <class Epi>
+  void launch_bn(int bn, const CUtensorMap& tmA, const Linear& W, const tc::GemmShape& s, const Epi& epi, cudaStream_t st) {
+    switch (bn) {
+      case 64: tc::launch<64, 8, Epi>(tmA, W.tm[0], s, epi, st); break;
+      case 128: tc::launch<128, 6, Epi>(tmA, W.tm[1], s, epi, st); break;
+      case 192: tc::launch<192, 5, Epi>(tmA, W.tm[2], s, epi, st); break;
+      case 256: tc::launch<256, 4, Epi>(tmA, W.tm[3], s, epi, st); break;
+      default: throw std::runtime_error("unsupported N tile");
+    }
   }
 
   // 3x3 / stride 1 / pad 1 conv as implicit GEMM through a 4-D tensor map (K loop = 9 taps x Cin/64)
@@ -275,12 +300,11 @@ struct rgrg_engine {
     s.tiles_w = Wd / 16;
     s.tiles_h = H / 8;
     s.m_tiles = B * s.tiles_w * s.tiles_h;
-    const int bn = (W.N <= 64) ? 64 : 128;
+    const int bn = pick_bn(s.m_tiles, W.N);
     s.n_tiles = ceil_div(W.N, bn);
     s.m_fastest = 0;
     CUtensorMap tmA = tc::make_tmap_nhwc(in, B, H, Wd, Cin);
-    if (bn == 128) tc::launch<128, 6, Epi>(tmA, W.tm128, s, epi, st);
-    else tc::launch<64, 4, Epi>(tmA, W.tm64, s, epi, st);
+    launch_bn(bn, tmA, W, s, epi, st);
     ++launches;
   }
 
@@ -788,7 +812,7 @@ struct rgrg_engine {
       ids.ensure(rr * (s + 1) * 4);
       unfinished.ensure(rr * 4);
       unf_count.ensure(static_cast<size_t>(s + 1) * 4);
-      step.ensure(4);
+      step.ensure(16);
       ws_rows = r;
       ws_slots = s;
       for (auto& g : step_graphs) cudaGraphExecDestroy(g.second);  // buffers moved: captured pointers are stale
@@ -806,14 +830,13 @@ struct rgrg_engine {
     gemm("lm_image_kv", img.as<bf16>(), R, ukv, e, st, true);
   }
 
-  // one decode step for `rows` rows; every kernel reads the step index from device memory.
-  // logits_out != null: lm_head stores fp32 logits there instead of the fused arg-max.
-  int decode_step(int rows, const dec::GreedyState& g, float* logits_out, cudaStream_t st) {
-    const int before = static_cast<int>(launches);
+  // transformer body of one decode step for `rows` rows (embedding .. final LayerNorm); every kernel reads the step
+  // index from device memory.  Leaves ln_f(h) as bf16 in `x`.
+  void decode_forward(int rows, const int* ids_ptr, int ids_ld, cudaStream_t st) {
     const int* sp = step.as<int>();
     {
       ProfScope ps(this, "embed", st);
-      dec::embed_kernel<<<rows, 256, 0, st>>>(wte_f32, g.ids, g.ids_ld, sp, h.as<float>());
+      dec::embed_kernel<<<rows, 256, 0, st>>>(wte_f32, ids_ptr, ids_ld, sp, h.as<float>());
       KERNEL_CHECK();
       ++launches;
     }
@@ -829,7 +852,8 @@ struct rgrg_engine {
       gemm("c_attn", x.as<bf16>(), rows, L.attn, eq, st, true);
       {
         ProfScope ps(this, "attention", st);
-        dec::attention_kernel<<<ceil_div(rows * 16, 4), 128, 0, st>>>(q.as<bf16>(), kv_geom(), l, sp, attn_o.as<bf16>(), rows);
+        dec::attention_kernel<<<ceil_div(rows * 16, 4), 128, 0, st>>>(q.as<bf16>(), kv_geom(), l, sp, attn_o.as<bf16>(), rows,
+                                                                      beam_anc, beam_slots, beam_nb);
         KERNEL_CHECK();
       }
       gemm("attn_c_proj", attn_o.as<bf16>(), rows, L.proj, store_f32(h.as<float>(), L.proj.bias, DM, ACT_NONE, h.as<float>()), st, true);
@@ -848,21 +872,196 @@ struct rgrg_engine {
       KERNEL_CHECK();
       ++launches;
     }
+  }
+
+  // one greedy decode step.  logits_out != null: lm_head stores fp32 logits there instead of the fused arg-max.
+  int decode_step(int rows, const dec::GreedyState& g, float* logits_out, cudaStream_t st) {
+    const int before = static_cast<int>(launches);
+    decode_forward(rows, g.ids, g.ids_ld, st);
     if (logits_out || opt_gemm_impl == 2) {
       float* dst = logits_out ? logits_out : logits_tmp.as<float>();
       gemm("lm_head", x.as<bf16>(), rows, lm_head, store_f32(dst, nullptr, VOCAB, ACT_NONE), st, true);
       ProfScope ps(this, "greedy_update", st);
-      dec::greedy_update_kernel<<<1, 1024, 0, st>>>(nullptr, nullptr, 0, dst, g, rows);
+      dec::greedy_update_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(nullptr, nullptr, 0, dst, g, rows);
     } else {
-      const int n_tiles = ceil_div(VOCAB, 128);
+      const int bn = pick_bn(ceil_div(rows, tc::BM), VOCAB);
+      const int n_tiles = ceil_div(VOCAB, bn);
       EpiArgmaxPartial ea{part_val.as<float>(), part_idx.as<int>(), n_tiles};
-      gemm("lm_head", x.as<bf16>(), rows, lm_head, ea, st, true, 128);
+      gemm("lm_head", x.as<bf16>(), rows, lm_head, ea, st, true, bn);
       ProfScope ps(this, "greedy_update", st);
-      dec::greedy_update_kernel<<<1, 1024, 0, st>>>(part_val.as<float>(), part_idx.as<int>(), n_tiles, nullptr, g, rows);
+      dec::greedy_update_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(part_val.as<float>(), part_idx.as<int>(), n_tiles, nullptr, g, rows);
     }
     KERNEL_CHECK();
     ++launches;
     return static_cast<int>(launches) - before;
+  }
+
+  // ================================================================================================================
+  // beam search (language_model.py:529-607; BeamSearchScorer restated from transformers 4.19.2)
+  // ================================================================================================================
+  DevBuf b_ids2, b_anc[2], b_scores, b_cand_score, b_cand_token, b_cand_beam, b_hyp_score, b_hyp_len, b_hyp_tok, b_hyp_count,
+      b_worst, b_done, b_not_done;
+
+  dec::BeamState beam_state(int sentences, int nb, int max_length, bool early) {
+    const size_t rows = static_cast<size_t>(sentences) * nb;
+    const int slots = max_length + 1;
+    b_ids2.ensure(rows * max_length * 4);
+    b_anc[0].ensure(rows * slots);
+    b_anc[1].ensure(rows * slots);
+    b_scores.ensure(rows * 4);
+    b_cand_score.ensure(rows * 2 * 4);
+    b_cand_token.ensure(rows * 2 * 4);
+    b_cand_beam.ensure(rows * 2 * 4);
+    b_hyp_score.ensure(rows * 4);
+    b_hyp_len.ensure(rows * 4);
+    b_hyp_tok.ensure(rows * max_length * 4);
+    b_hyp_count.ensure(static_cast<size_t>(sentences) * 4);
+    b_worst.ensure(static_cast<size_t>(sentences) * 4);
+    b_done.ensure(static_cast<size_t>(sentences) * 4);
+    b_not_done.ensure(static_cast<size_t>(max_length + 1) * 4);
+    dec::BeamState s{};
+    s.nb = nb;
+    s.ids_ld = max_length;
+    s.ids[0] = ids.as<int>();
+    s.ids[1] = b_ids2.as<int>();
+    s.anc[0] = b_anc[0].as<unsigned char>();
+    s.anc[1] = b_anc[1].as<unsigned char>();
+    s.slots = slots;
+    s.beam_scores = b_scores.as<float>();
+    s.cand_score = b_cand_score.as<float>();
+    s.cand_token = b_cand_token.as<int>();
+    s.cand_beam = b_cand_beam.as<int>();
+    s.hyp_score = b_hyp_score.as<float>();
+    s.hyp_len = b_hyp_len.as<int>();
+    s.hyp_tok = b_hyp_tok.as<int>();
+    s.hyp_count = b_hyp_count.as<int>();
+    s.worst = b_worst.as<float>();
+    s.done = b_done.as<int>();
+    s.not_done_count = b_not_done.as<int>();
+    s.step_ptr = step.as<int>();
+    s.early_stopping = early ? 1 : 0;
+    return s;
+  }
+
+  void beam_bookkeeping(const dec::BeamState& s, const float* logits, int sentences, int src, cudaStream_t st) {
+    ProfScope ps(this, "beam_bookkeeping", st);
+    dec::beam_topk_kernel<<<sentences, 1024, 0, st>>>(logits, s);
+    KERNEL_CHECK();
+    dec::beam_process_kernel<<<ceil_div(sentences, 64), 64, 0, st>>>(s, sentences, src, src ^ 1);
+    KERNEL_CHECK();
+    dec::beam_step_end_kernel<<<1, 256, 0, st>>>(s, sentences);
+    KERNEL_CHECK();
+    launches += 3;
+  }
+
+  // BeamSearchScorer.finalize on the host (once per generate); returns the reference width
+  int beam_finalize(const dec::BeamState& s, int sentences, int cur_len, int final_buf, int max_length, int32_t* out_ids,
+                    cudaStream_t st) {
+    const int nb = s.nb;
+    const size_t rows = static_cast<size_t>(sentences) * nb;
+    std::vector<int> h_ids(rows * max_length), h_hyp_tok(rows * max_length), h_hyp_len(rows), h_count(sentences), h_done(sentences);
+    std::vector<float> h_scores(rows), h_hyp_score(rows), h_worst(sentences);
+    CUDA_CHECK(cudaMemcpyAsync(h_ids.data(), s.ids[final_buf], h_ids.size() * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(h_hyp_tok.data(), s.hyp_tok, h_hyp_tok.size() * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(h_hyp_len.data(), s.hyp_len, rows * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(h_hyp_score.data(), s.hyp_score, rows * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(h_scores.data(), s.beam_scores, rows * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(h_count.data(), s.hyp_count, sentences * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(h_done.data(), s.done, sentences * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(h_worst.data(), s.worst, sentences * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    struct Hyp {
+      float score;
+      std::vector<int> tok;
+    };
+    std::vector<std::vector<int>> best(sentences);
+    int max_len = 0, min_len = 1 << 30;
+    for (int i = 0; i < sentences; ++i) {
+      std::vector<Hyp> beams;
+      for (int k = 0; k < h_count[i]; ++k) {
+        const int* t = h_hyp_tok.data() + (static_cast<size_t>(i) * nb + k) * max_length;
+        beams.push_back(Hyp{h_hyp_score[i * nb + k], std::vector<int>(t, t + h_hyp_len[i * nb + k])});
+      }
+      float worst = h_worst[i];
+      if (!h_done[i]) {  // all open beams become hypotheses (BeamHypotheses.add)
+        for (int b = 0; b < nb; ++b) {
+          const int* t = h_ids.data() + (static_cast<size_t>(i) * nb + b) * max_length;
+          const float score = h_scores[i * nb + b] / static_cast<float>(cur_len);
+          if (static_cast<int>(beams.size()) < nb || score > worst) {
+            beams.push_back(Hyp{score, std::vector<int>(t, t + cur_len)});
+            if (static_cast<int>(beams.size()) > nb) {
+              size_t lo = 0;
+              for (size_t k = 1; k < beams.size(); ++k)
+                if (beams[k].score < beams[lo].score) lo = k;
+              beams.erase(beams.begin() + lo);
+              worst = beams[0].score;
+              for (const Hyp& hh : beams) worst = std::min(worst, hh.score);
+            } else {
+              worst = std::min(score, worst);
+            }
+          }
+        }
+      }
+      // sorted(beams, key=score) is stable; pop() takes the last of the highest score
+      size_t pick = 0;
+      for (size_t k = 1; k < beams.size(); ++k)
+        if (beams[k].score >= beams[pick].score) pick = k;
+      best[i] = beams.empty() ? std::vector<int>() : beams[pick].tok;
+      max_len = std::max<int>(max_len, static_cast<int>(best[i].size()));
+      min_len = std::min<int>(min_len, static_cast<int>(best[i].size()));
+    }
+    const int width = std::min(max_len + 1, max_length);
+    for (int i = 0; i < sentences; ++i) {
+      int32_t* row = out_ids + static_cast<size_t>(i) * max_length;
+      for (int c = 0; c < max_length; ++c) row[c] = RGRG_EOS;
+      const int len = static_cast<int>(best[i].size());
+      for (int c = 0; c < len && c < max_length; ++c) row[c] = best[i][c];
+      if (len < width) row[len] = RGRG_EOS;
+    }
+    return width;
+  }
+
+  int run_beam(const bf16* feats_bf16, int R, int nb, int max_length, bool early, int32_t* out_ids, cudaStream_t st) {
+    if (nb > dec::MAX_BEAMS) throw std::runtime_error("num_beams > 8 is not supported");
+    const int rows = R * nb;
+    ensure_decoder_ws(rows, max_length);
+    logits_tmp.ensure(static_cast<size_t>(rows) * VOCAB * 4);
+    dec::BeamState s = beam_state(R, nb, max_length, early);
+    lm_prologue(feats_bf16, R, nb, st);
+    dec::beam_init_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(s, R);
+    KERNEL_CHECK();
+    ++launches;
+    const int steps = max_length - 1;
+    int cur = 0, done_steps = 0;
+    beam_slots = s.slots;
+    beam_nb = nb;
+    for (int t = 0; t < steps; ++t) {
+      beam_anc = s.anc[cur];
+      decode_forward(rows, s.ids[cur], max_length, st);
+      gemm("lm_head", x.as<bf16>(), rows, lm_head, store_f32(logits_tmp.as<float>(), nullptr, VOCAB, ACT_NONE), st, true);
+      beam_bookkeeping(s, logits_tmp.as<float>(), R, cur, st);
+      cur ^= 1;
+      ++done_steps;
+      if ((t & 7) == 7 && t + 1 < steps) {  // beam_scorer.is_done (language_model.py:594) without a per-step sync
+        int c = 1;
+        CUDA_CHECK(cudaMemcpyAsync(&c, s.not_done_count + t, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (c == 0) break;
+      }
+    }
+    beam_anc = nullptr;
+    beam_nb = 1;
+    // the reference leaves the loop right after the first step at which every sentence is done; later steps only pad
+    std::vector<int> nd(done_steps > 0 ? done_steps : 1);
+    CUDA_CHECK(cudaMemcpyAsync(nd.data(), s.not_done_count, static_cast<size_t>(done_steps) * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    int cur_len = done_steps + 1;
+    for (int t = 0; t < done_steps; ++t)
+      if (nd[t] == 0) {
+        cur_len = t + 2;
+        break;
+      }
+    return beam_finalize(s, R, cur_len, cur, max_length, out_ids, st);
   }
 
   // greedy decode of `R` rows whose features sit in feats_bf16; host ids [R, max_length], returns reference width
@@ -876,7 +1075,8 @@ struct rgrg_engine {
     g.unfinished = unfinished.as<int>();
     g.unfinished_count = unf_count.as<int>();
     g.step_ptr = step.as<int>();
-    dec::greedy_init_kernel<<<ceil_div(R, 256), 256, 0, st>>>(g, R);
+    g.ticket = step.as<int>() + 1;
+    dec::greedy_init_kernel<<<ceil_div(std::max(R, max_length), 256), 256, 0, st>>>(g, R);
     KERNEL_CHECK();
     ++launches;
     const int steps = max_length - 1;
@@ -1093,15 +1293,16 @@ int rgrg_generate(rgrg_engine_t* e, const float* images, int images_on_host, int
                   uint8_t* out_detected, float* out_boxes, float* out_scores, int* out_R, void* stream) {
   RGRG_TRY(e, {
     check_ready(e);
-    if (num_beams != 1) throw std::runtime_error("beam search is not available in this build (num_beams must be 1)");
+    if (num_beams < 1) throw std::runtime_error("num_beams must be >= 1");
     if (max_length < 2 || max_length > 1024) throw std::runtime_error("max_length must be in [2, 1024]");
-    (void)early_stopping;
     cudaStream_t st = e->enter(stream);
     const float* img = stage_images(e, images, images_on_host, B, S, st);
     const int R = e->run_detect(img, B, S, st);
     *out_R = R;
     int width = 0;
-    if (R > 0) width = e->run_greedy(e->lm_in.as<bf16>(), R, max_length, out_ids, st);
+    if (R > 0)
+      width = num_beams == 1 ? e->run_greedy(e->lm_in.as<bf16>(), R, max_length, out_ids, st)
+                             : e->run_beam(e->lm_in.as<bf16>(), R, num_beams, max_length, early_stopping != 0, out_ids, st);
     if (out_width) *out_width = width;
     read_detections(e, B, out_selected, out_detected, out_boxes, out_scores, nullptr, nullptr, nullptr, st);
   });
@@ -1126,13 +1327,13 @@ int rgrg_lm_generate(rgrg_engine_t* e, const float* feats, int feats_on_host, in
                      int early_stopping, int32_t* out_ids, int* out_width, void* stream) {
   RGRG_TRY(e, {
     check_ready(e);
-    if (num_beams != 1) throw std::runtime_error("beam search is not available in this build (num_beams must be 1)");
+    if (num_beams < 1) throw std::runtime_error("num_beams must be >= 1");
     if (max_length < 2 || max_length > 1024) throw std::runtime_error("max_length must be in [2, 1024]");
     if (R <= 0) throw std::runtime_error("R must be positive");
-    (void)early_stopping;
     cudaStream_t st = e->enter(stream);
     const bf16* f = stage_feats(e, feats, feats_on_host, R, st);
-    const int width = e->run_greedy(f, R, max_length, out_ids, st);
+    const int width = num_beams == 1 ? e->run_greedy(f, R, max_length, out_ids, st)
+                                     : e->run_beam(f, R, num_beams, max_length, early_stopping != 0, out_ids, st);
     if (out_width) *out_width = width;
   });
 }
@@ -1151,12 +1352,40 @@ int rgrg_lm_forced_logits(rgrg_engine_t* e, const float* feats_dev, int R, const
     g.unfinished = e->unfinished.as<int>();
     g.unfinished_count = e->unf_count.as<int>();
     g.step_ptr = e->step.as<int>();
+    g.ticket = e->step.as<int>() + 1;
     g.forced = forced_ids_dev;
-    dec::greedy_init_kernel<<<ceil_div(R, 256), 256, 0, st>>>(g, R);
+    dec::greedy_init_kernel<<<ceil_div(std::max(R, n_tokens), 256), 256, 0, st>>>(g, R);
     KERNEL_CHECK();
     ++e->launches;
     for (int t = 0; t < n_tokens; ++t) e->decode_step(R, g, out_logits_dev + static_cast<size_t>(t) * R * VOCAB, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int rgrg_beam_bookkeeping(rgrg_engine_t* e, const float* logits_steps_dev, int n_steps, int sentences, int num_beams,
+                          int max_length, int early_stopping, int32_t* out_ids, int* out_width, void* stream) {
+  RGRG_TRY(e, {
+    cudaStream_t st = e->enter(stream);
+    if (num_beams > dec::MAX_BEAMS || num_beams < 2) throw std::runtime_error("num_beams must be in [2, 8]");
+    const int rows = sentences * num_beams;
+    e->ensure_decoder_ws(rows, max_length);
+    dec::BeamState s = e->beam_state(sentences, num_beams, max_length, early_stopping != 0);
+    dec::beam_init_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(s, sentences);
+    KERNEL_CHECK();
+    int cur = 0;
+    int cur_len = 1;
+    std::vector<int> nd(n_steps);
+    for (int t = 0; t < n_steps && t < max_length - 1; ++t) {
+      e->beam_bookkeeping(s, logits_steps_dev + static_cast<size_t>(t) * rows * VOCAB, sentences, cur, st);
+      cur ^= 1;
+      ++cur_len;
+      int c = 1;
+      CUDA_CHECK(cudaMemcpyAsync(&c, s.not_done_count + t, 4, cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      if (c == 0) break;
+    }
+    const int width = e->beam_finalize(s, sentences, cur_len, cur, max_length, out_ids, st);
+    if (out_width) *out_width = width;
   });
 }
 
@@ -1227,7 +1456,8 @@ int rgrg_gemm_bf16(rgrg_engine_t* e, const void* A_dev, const void* W_dev, const
     e->opt_gemm_impl = impl == 2 ? 2 : 0;
     try {
       if (impl != 2) L.make_maps();
-      e->gemm("test_gemm", static_cast<const bf16*>(A_dev), M, L, ep, st, true, impl == 0 ? 128 : (impl == 1 ? 64 : 0));
+      e->gemm("test_gemm", static_cast<const bf16*>(A_dev), M, L, ep, st, true,
+              impl == 0 ? 128 : impl == 1 ? 64 : impl == 3 ? 192 : impl == 4 ? 256 : 0);
     } catch (...) {
       e->opt_gemm_impl = saved;
       throw;

@@ -1,8 +1,10 @@
 // Fused GEMM epilogues.  A functor sees one output row and NV consecutive accumulator columns at a time:
-//   init(State&)                                   once per thread-row
+//   init(State&)                                   once per thread and tile
 //   apply<NV>(State&, row, col0, const float* v, N)   v[j] = D[row, col0 + j]; columns >= N are padding
-//   finish(State&, row, n_blk)                     once per thread-row after the last chunk of the tile
-// The tcgen05 kernel calls apply<32> (one TMEM lane = one row per thread); the SIMT kernel calls apply<4>.
+//   finish(State&, row, n_blk)                     kDirect functors only: once per row after the tile's last chunk
+// The tcgen05 kernel calls apply<8> after its shared-memory transpose (a lane owns 8 consecutive columns, 4 lanes cover
+// a 128-byte fp32 row segment) or, for kDirect functors (reductions along N), apply<32> with one row per thread;
+// the CUDA-core kernel calls apply<4>.
 #pragma once
 #include "common.cuh"
 
@@ -14,6 +16,7 @@ enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU_NEW = 2 };
 // (decoder residual stream; out_f32 may alias res_f32 — each element is read then written by the same thread).
 struct EpiStore {
   struct State {};
+  static constexpr bool kDirect = false;
   float* out_f32;
   bf16* out_bf16;
   const float* bias;     // [N] or null
@@ -80,6 +83,7 @@ struct KvGeom {
 // [1024,2048) -> K cache, [2048,3072) -> V cache, appended in place at slot *step_ptr + 1.
 struct EpiQkvAppend {
   struct State {};
+  static constexpr bool kDirect = false;
   bf16* q_out;        // [M, 1024]
   const float* bias;  // [3072]
   KvGeom kv;
@@ -118,6 +122,7 @@ struct EpiQkvAppend {
 // column n -> layer n/2048, k/v (n/1024)&1, head (n&1023)/64; written to cache slot 0 of every beam of the row.
 struct EpiImageKv {
   struct State {};
+  static constexpr bool kDirect = false;
   const float* bias;  // [49152]
   KvGeom kv;
   int beams;
@@ -154,6 +159,7 @@ struct EpiArgmaxPartial {
     float best;
     int idx;
   };
+  static constexpr bool kDirect = true;  // reduction along N: one row per thread, no transpose
   float* part_val;  // [M, n_tiles]
   int* part_idx;    // [M, n_tiles]
   int n_tiles;

@@ -1,9 +1,8 @@
 // tcgen05 + TMA GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T   (bf16 operands, fp32 accumulate in TMEM)
 //
-// One CTA = one 128 x BN output tile.  Warp roles (192 threads):
-//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem stages, mbarrier complete_tx)
-//   warp 1      : TMEM allocator + MMA issuer (one elected lane issues tcgen05.mma, tcgen05.commit frees stages)
-//   warps 2..5  : epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue functor -> global)
+// Persistent: one CTA per SM walks 128 x BN output tiles; two TMEM accumulator stages overlap the epilogue of one
+// tile with the main loop of the next.  Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA
+// issuer, warps 2..5 epilogue (see the kernel).
 //
 // Operand A is fetched either through a 2-D tensor map over a row-major [M,K] matrix (plain GEMM: every Linear /
 // Conv1D / 1x1 conv of the path) or through a 4-D tensor map over an NHWC activation (implicit-GEMM 3x3 conv,
@@ -151,22 +150,61 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int EPI_WARPS = 4;
+constexpr int STG_LD = 36;  // staging row stride in floats (32 + 4): 16-byte aligned rows, conflict-free quarter-warps
+
 template <int BN, int STAGES>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
+  static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
+  static_assert(TOTAL <= 232448, "shared memory budget exceeded");
+  static_assert(TOTAL > 116 * 1024, "must stay above half an SM's smem: exactly one CTA per SM may own TMEM");
 };
 
 template <int BN>
-constexpr int tmem_cols() {
-  return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
+constexpr int tmem_cols() {  // two accumulator stages, power of two >= 32
+  return 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;
+}
+
+struct TileCoord {
+  int m_blk, n_blk, img, h0, w0;
+};
+__device__ __forceinline__ TileCoord tile_coord(const GemmShape& s, int tile) {
+  TileCoord c;
+  if (s.m_fastest) {
+    c.m_blk = tile % s.m_tiles;
+    c.n_blk = tile / s.m_tiles;
+  } else {
+    c.n_blk = tile % s.n_tiles;
+    c.m_blk = tile / s.n_tiles;
+  }
+  c.img = c.h0 = c.w0 = 0;
+  if (s.conv) {  // decompose the M tile into (image, 8x16 pixel patch)
+    const int per_img = s.tiles_w * s.tiles_h;
+    c.img = c.m_blk / per_img;
+    const int t = c.m_blk - c.img * per_img;
+    c.h0 = (t / s.tiles_w) * 8;
+    c.w0 = (t % s.tiles_w) * 16;
+  }
+  return c;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The kernel
+// The kernel: persistent (one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...), two TMEM accumulator stages so
+// the epilogue of tile i overlaps the main loop of tile i+1.
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + MMA issuer (one lane issues tcgen05.mma; tcgen05.commit frees ring slots)
+//   warps 2..5  : epilogue: tcgen05.ld 32x32b (lane = row) -> smem transpose -> 8 consecutive columns per lane
+//                 -> fused epilogue functor with 16-byte coalesced global accesses
 // ---------------------------------------------------------------------------------------------------------------
 template <int BN, int STAGES, class Epi>
 __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -177,29 +215,13 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  int m_blk, n_blk;
-  if (s.m_fastest) {
-    m_blk = blockIdx.x % s.m_tiles;
-    n_blk = blockIdx.x / s.m_tiles;
-  } else {
-    n_blk = blockIdx.x % s.n_tiles;
-    m_blk = blockIdx.x / s.n_tiles;
-  }
-  // conv mode: decompose the M tile into (image, 8x16 pixel patch)
-  int img = 0, h0 = 0, w0 = 0;
-  if (s.conv) {
-    const int per_img = s.tiles_w * s.tiles_h;
-    img = m_blk / per_img;
-    const int t = m_blk - img * per_img;
-    h0 = (t / s.tiles_w) * 8;
-    w0 = (t % s.tiles_w) * 16;
-  }
+  const int num_tiles = s.m_tiles * s.n_tiles;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -209,7 +231,11 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], EPI_WARPS);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -223,69 +249,136 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < s.k_iters; ++kb) {
-        const int st = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[st], ph ^ 1);
-        mbar_expect_tx(&full_bar[st], L::STAGE_BYTES);
-        uint8_t* a_dst = smem + st * L::STAGE_BYTES;
-        uint8_t* b_dst = a_dst + L::A_BYTES;
-        if (s.conv) {
-          const int tap = kb / s.kc_blocks;
-          const int kc = kb - tap * s.kc_blocks;
-          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-          tma_load_4d(a_dst, &tmA, &full_bar[st], kc * BK, w0 + dx, h0 + dy, img);
-        } else {
-          tma_load_2d(a_dst, &tmA, &full_bar[st], kb * BK, m_blk * BM);
+      int kbg = 0;  // k-block counter across tiles: ring slot = kbg % STAGES
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord tc_ = tile_coord(s, tile);
+        for (int kb = 0; kb < s.k_iters; ++kb, ++kbg) {
+          const int st = kbg % STAGES;
+          const uint32_t ph = (kbg / STAGES) & 1;
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          mbar_expect_tx(&full_bar[st], L::STAGE_BYTES);
+          uint8_t* a_dst = smem + st * L::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + L::A_BYTES;
+          if (s.conv) {
+            const int tap = kb / s.kc_blocks;
+            const int kc = kb - tap * s.kc_blocks;
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            tma_load_4d(a_dst, &tmA, &full_bar[st], kc * BK, tc_.w0 + dx, tc_.h0 + dy, tc_.img);
+          } else {
+            tma_load_2d(a_dst, &tmA, &full_bar[st], kb * BK, tc_.m_blk * BM);
+          }
+          tma_load_2d(b_dst, &tmB, &full_bar[st], kb * BK, tc_.n_blk * BN);
         }
-        tma_load_2d(b_dst, &tmB, &full_bar[st], kb * BK, n_blk * BN);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-      for (int kb = 0; kb < s.k_iters; ++kb) {
-        const int st = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[st], ph);
+      int kbg = 0, it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + st * L::STAGE_BYTES);
-        const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
-        const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + L::A_BYTES);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < s.k_iters; ++kb, ++kbg) {
+          const int st = kbg % STAGES;
+          const uint32_t ph = (kbg / STAGES) & 1;
+          mbar_wait(&full_bar[st], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + st * L::STAGE_BYTES);
+          const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
+          const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + L::A_BYTES);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[st]);  // ring slot reusable once these MMAs have read it
         }
-        umma_commit(&empty_bar[st]);  // stage reusable once these MMAs have read it
+        umma_commit(&tmem_full_bar[acc]);  // accumulator stage complete
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     const int q = warp & 3;  // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
-    const int r = q * 32 + lane;
-    int row;
-    bool row_ok;
-    if (s.conv) {
-      row = (img * s.H + h0 + (r >> 4)) * s.W + w0 + (r & 15);
-      row_ok = true;
-    } else {
-      row = m_blk * BM + r;
-      row_ok = row < s.M;
-    }
-    typename Epi::State st;
-    epi.init(st);
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+    float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET) + (warp - 2) * 32 * STG_LD;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const TileCoord tc_ = tile_coord(s, tile);
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      if constexpr (Epi::kDirect) {
+        // one row per thread, straight from registers (reductions along N: the arg-max epilogue)
+        const int r = q * 32 + lane;
+        int row;
+        bool row_ok;
+        if (s.conv) {
+          row = (tc_.img * s.H + tc_.h0 + (r >> 4)) * s.W + tc_.w0 + (r & 15);
+          row_ok = true;
+        } else {
+          row = tc_.m_blk * BM + r;
+          row_ok = row < s.M;
+        }
+        typename Epi::State st;
+        epi.init(st);
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, v);
-      tmem_ld_wait();
-      const int col0 = n_blk * BN + c;
-      if (row_ok && col0 < s.N) epi.template apply<32>(st, row, col0, reinterpret_cast<const float*>(v), s.N);
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_addr + c, v);
+          tmem_ld_wait();
+          const int col0 = tc_.n_blk * BN + c;
+          if (row_ok && col0 < s.N) epi.template apply<32>(st, row, col0, reinterpret_cast<const float*>(v), s.N);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        if (row_ok) epi.finish(st, row, tc_.n_blk);
+      } else {
+        typename Epi::State st;
+        epi.init(st);
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_addr + c, v);
+          tmem_ld_wait();
+          if (c + 32 >= BN) {  // last read of this accumulator stage: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          // transpose through shared memory: thread = row  ->  lane = 8 consecutive columns of 8 rows per pass
+          float4* dst = reinterpret_cast<float4*>(stg + lane * STG_LD);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                 __uint_as_float(v[4 * j + 3]));
+          __syncwarp();
+          const int col0 = tc_.n_blk * BN + c + (lane & 3) * 8;
+#pragma unroll
+          for (int pass = 0; pass < 4; ++pass) {
+            const int rl = pass * 8 + (lane >> 2);  // row within this warp's 32
+            const int r = q * 32 + rl;
+            int row;
+            bool row_ok;
+            if (s.conv) {
+              row = (tc_.img * s.H + tc_.h0 + (r >> 4)) * s.W + tc_.w0 + (r & 15);
+              row_ok = true;
+            } else {
+              row = tc_.m_blk * BM + r;
+              row_ok = row < s.M;
+            }
+            const float4* src = reinterpret_cast<const float4*>(stg + rl * STG_LD + (lane & 3) * 8);
+            const float4 x0 = src[0], x1 = src[1];
+            const float vals[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            if (row_ok && col0 < s.N) epi.template apply<8>(st, row, col0, vals, s.N);
+          }
+          __syncwarp();
+        }
+      }
     }
-    if (row_ok) epi.finish(st, row, n_blk);
   }
   tc_fence_before();
   __syncthreads();
@@ -338,6 +431,16 @@ inline CUtensorMap make_tmap_nhwc(const void* ptr, uint64_t N, uint64_t H, uint6
   return m;
 }
 
+inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
 template <int BN, int STAGES, class Epi>
 inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const Epi& epi,
                    cudaStream_t stream) {
@@ -348,7 +451,9 @@ inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmSha
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  kern<<<s.m_tiles * s.n_tiles, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, s, epi);
+  const int tiles = s.m_tiles * s.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, s, epi);
   KERNEL_CHECK();
 }
 

@@ -138,6 +138,16 @@ class Engine:
                                                     _stream(self.device)))
         return out
 
+    def beam_bookkeeping(self, logits_steps: torch.Tensor, sentences: int, num_beams: int, max_length: int,
+                         early_stopping: bool):
+        n_steps = int(logits_steps.shape[0])
+        ids = np.full((sentences, max_length), EOS, dtype=np.int32)
+        width = C.c_int(0)
+        self._check(self._lib.rgrg_beam_bookkeeping(self._h, _ptr(logits_steps.contiguous()), n_steps, sentences, num_beams,
+                                                    max_length, int(bool(early_stopping)), _ptr(ids), C.byref(width),
+                                                    _stream(self.device)))
+        return ids[:, : width.value]
+
     def rpn_filter(self, objectness, deltas=None, decoded=None, feat=16, image_size=512):
         B = int(objectness.shape[0])
         dev = objectness.device

@@ -20,7 +20,7 @@ def _rand_bf16(shape, seed, scale=1.0):
     return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).cuda()
 
 
-@pytest.mark.parametrize("impl", [2, 0, 1])
+@pytest.mark.parametrize("impl", [2, 0, 1, 3, 4])  # CUDA-core check, tcgen05 N tile 128 / 64 / 192 / 256
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (300, 200, 192), (928, 3072, 1024), (37, 800, 2048),
                                    (257, 50257, 1024), (1000, 64, 576)])
 def test_gemm_matches_fp32_math(eng_bare, impl, M, N, K):
@@ -125,3 +125,45 @@ def test_roi_tail_bit_exact_on_reference_vectors(eng, golden):
     assert torch.equal(idx.cpu().long(), T(g["top_idx"]))
     assert torch.allclose(scores.cpu(), T(g["top_scores"]), rtol=1e-5, atol=1e-7)
     assert torch.allclose(tb.cpu(), T(g["top_region_boxes"]), rtol=0, atol=2e-3)
+
+
+# ---- beam-search bookkeeping (K24-K26): device top-k / BeamSearchScorer.process / finalize against the reference loop
+def _reference_beam_loop(logits_steps, sentences, nb, max_length, early):
+    """language_model.py:545-607 with the model forward replaced by given logits; scorer = oracle/beam_scorer.py."""
+    from beam_scorer import BeamSearchScorer
+
+    V = logits_steps.shape[-1]
+    scorer = BeamSearchScorer(batch_size=sentences, num_beams=nb, device=torch.device("cpu"), length_penalty=1.0,
+                              do_early_stopping=early, num_beam_hyps_to_keep=1)
+    ids = torch.full((sentences * nb, 1), 50256, dtype=torch.int64)
+    beam_scores = torch.zeros(sentences, nb)
+    beam_scores[:, 1:] = -1e9
+    beam_scores = beam_scores.view(-1)
+    cur_len = 1
+    for t in range(logits_steps.shape[0]):
+        scores = torch.log_softmax(logits_steps[t], dim=-1) + beam_scores[:, None]
+        scores, tokens = torch.topk(scores.view(sentences, nb * V), 2 * nb, dim=1, largest=True, sorted=True)
+        indices = torch.div(tokens, V, rounding_mode="floor")
+        tokens = tokens % V
+        out = scorer.process(ids, scores, tokens, indices, pad_token_id=50256, eos_token_id=50256)
+        beam_scores = out["next_beam_scores"]
+        ids = torch.cat([ids[out["next_beam_indices"], :], out["next_beam_tokens"].unsqueeze(-1)], dim=-1)
+        cur_len += 1
+        if scorer.is_done or cur_len >= max_length:
+            break
+    return scorer.finalize(ids, beam_scores, tokens, indices, pad_token_id=50256, eos_token_id=50256,
+                           max_length=max_length)["sequences"]
+
+
+@pytest.mark.parametrize("early", [True, False])
+@pytest.mark.parametrize("eos_rate", [0.0, 0.15, 0.6])
+def test_beam_bookkeeping_matches_reference_loop(eng_bare, early, eos_rate):
+    sentences, nb, T, V = 5, 4, 9, 50257
+    g = torch.Generator().manual_seed(int(eos_rate * 100) + int(early))
+    logits = torch.randn(T - 1, sentences * nb, V, generator=g) * 2.0
+    boost = torch.rand(T - 1, sentences * nb, generator=g) < eos_rate
+    logits[:, :, 50256] = torch.where(boost, torch.full_like(logits[:, :, 0], 14.0), logits[:, :, 50256])
+    ref = _reference_beam_loop(logits, sentences, nb, T, early)
+    out = eng_bare.beam_bookkeeping(logits.cuda(), sentences, nb, T, early)
+    assert out.shape == tuple(ref.shape), (out.shape, ref.shape)
+    assert np.array_equal(out.astype(np.int64), ref.numpy())

@@ -114,3 +114,15 @@ def test_gemm_cross_check_path_agrees(model, images):
     eng.set_option("gemm_impl", 0)
     assert np.array_equal(a["detected"], b["detected"])
     assert _rel(torch.from_numpy(a["region_features"]), torch.from_numpy(b["region_features"])) < 0.2
+
+
+def test_beam_search_end_to_end_contract(model, synth_sd, oracle_detail):
+    """Beam search through the reference-facing API.  Free-running bf16 vs fp32 beams may branch on near-ties, so the
+    bit-exact check of the bookkeeping is teacher-forced (tests/test_gpu_kernels.py); here: contract + the first token,
+    whose score gaps at step 0 are decided by the BOS logits alone."""
+    feats = oracle_detail["sel_feats"][:3].contiguous()
+    ref = O.lm_generate(synth_sd, feats, max_length=6, num_beams=4, early_stopping=True)
+    ids = model.language_model.generate(feats.cuda(), max_length=6, num_beams=4, early_stopping=True)
+    assert ids.shape == ref.shape and ids.dtype == torch.int64
+    assert (ids[:, 0] == 50256).all()
+    assert (ids.cpu() == ref).float().mean().item() > 0.5

@@ -67,8 +67,8 @@ def main():
     elif step == "tc_shapes":
         for (M, N, K) in [(300, 200, 192), (928, 3072, 1024), (37, 800, 2048), (257, 50257, 1024), (1000, 64, 576),
                           (4096, 1024, 4096)]:
-            gemm_case(e, M, N, K, 0)
-            gemm_case(e, M, N, K, 1)
+            for impl in (0, 1, 3, 4):
+                gemm_case(e, M, N, K, impl)
     elif step == "conv":
         for implicit in (False, True):
             for (B, H, Cin, Cout) in [(2, 16, 64, 64), (1, 32, 128, 128), (2, 16, 2048, 256), (1, 128, 64, 64)]:
@@ -80,20 +80,19 @@ def main():
                                                  padding=1).permute(0, 2, 3, 1)
                 report("conv3x3 implicit=%d B=%d H=%d Cin=%d Cout=%d" % (implicit, B, H, Cin, Cout), out, ref)
     elif step == "gemm_perf":
-        for (M, N, K, impl) in [(928, 3072, 1024, 0), (928, 1024, 1024, 1), (928, 4096, 1024, 0), (928, 1024, 4096, 1),
-                                (928, 50257, 1024, 0), (8192, 8192, 8192, 0), (27200, 1024, 8192, 0)]:
+        cases = [(928, 3072, 1024, i) for i in (0, 1, 3, 4)] + [(928, 1024, 1024, 1), (928, 4096, 1024, 4), (928, 1024, 4096, 1),
+                 (928, 50257, 1024, 4)] + [(8192, 8192, 8192, i) for i in (0, 3, 4)] + [(27200, 1024, 8192, 4)]
+        for (M, N, K, impl) in cases:
             A, W = rnd((M, K), 1), rnd((N, K), 2, 0.05)
             for _ in range(3):
                 out = e.gemm(A, W, None, 0, impl)
-            torch.cuda.synchronize()
-            ev0, ev1 = torch.cuda.Event(True), torch.cuda.Event(True)
-            ev0.record()
+            e.set_option("profile", 1)
             for _ in range(10):
                 out = e.gemm(A, W, None, 0, impl)
-            ev1.record()
-            torch.cuda.synchronize()
-            ms = ev0.elapsed_time(ev1) / 10
-            print("perf impl=%d M=%d N=%d K=%d: %.3f ms  %.1f TFLOP/s (incl. sync + fp32 store)" %
+            ms, n = e.profile_read()["test_gemm"]
+            e.set_option("profile", 0)
+            ms /= n
+            print("perf impl=%d M=%d N=%d K=%d: %.4f ms  %.1f TFLOP/s (CUDA events around the kernel, fp32 store epilogue)" %
                   (impl, M, N, K, ms, 2.0 * M * N * K / ms / 1e9), flush=True)
     print("step %s done" % step, flush=True)
 
