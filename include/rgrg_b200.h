@@ -119,6 +119,11 @@ RGRG_API int rgrg_roi_tail(rgrg_engine_t* e, const float* class_logits_dev, cons
 RGRG_API int rgrg_gemm_bf16(rgrg_engine_t* e, const void* A_dev, const void* W_dev, const float* bias_dev, int M, int N, int K,
                    int act, int impl, float* out_dev, void* stream);
 
+/* tuning harness: iters back-to-back launches of one bf16 GEMM (N tile `bn`), optionally interleaved with a LayerNorm launch;
+ * out_ms = average device time per iteration; trace_host (optional) = [trace_ctas, 8] clock64 timeline of the last launch */
+RGRG_API int rgrg_gemm_bench(rgrg_engine_t* e, int M, int N, int K, int bn, int iters, int interleave, float* out_ms,
+                    long long* trace_host, int trace_ctas);
+
 /* 3x3 / pad 1 / stride 1 conv, NHWC: in bf16 dev [B,H,W,Cin]; w bf16 dev [Cout, 9*Cin] (tap-major); out fp32 dev
  * [B,H,W,Cout].  implicit: 1 = TMA implicit GEMM (4-D tensor map, OOB zero fill), 0 = im2col + GEMM. */
 RGRG_API int rgrg_conv3x3_bf16(rgrg_engine_t* e, const void* in_dev, const void* w_dev, const float* bias_dev, int B, int H,
@@ -132,7 +137,7 @@ RGRG_API int rgrg_backbone(rgrg_engine_t* e, const float* images_dev, int B, int
 RGRG_API int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst, size_t bytes);
 
 /* behaviour switches: "implicit_conv" (0/1), "cuda_graph" (0/1), "gemm_impl" (0 tcgen05, 2 CUDA-core cross-check),
- * "profile" (0/1: record CUDA events around every kernel category on the launch stream; disables graph replay) */
+ * "pdl" (0/1: programmatic dependent launch between the kernels of a decode step), "profile" (0/1: record CUDA events around every kernel category on the launch stream; disables graph replay) */
 RGRG_API int rgrg_set_option(rgrg_engine_t* e, const char* key, int value);
 
 /* per-category device time since "profile" was switched on: text lines "<category> <total ms> <launches>\n" */

@@ -27,6 +27,7 @@ _PROTOTYPES = {
     "rgrg_roi_align": (_i, [c_p, c_p, c_p, c_p, _i, _i, _i, _i, c_p, c_p]),
     "rgrg_roi_tail": (_i, [c_p, c_p, c_p, c_p, c_p, _i, _i, c_p, c_p, c_p, c_p, c_p]),
     "rgrg_gemm_bf16": (_i, [c_p, c_p, c_p, c_p, _i, _i, _i, _i, _i, c_p, c_p]),
+    "rgrg_gemm_bench": (_i, [c_p, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_float), c_p, _i]),
     "rgrg_conv3x3_bf16": (_i, [c_p, c_p, c_p, c_p, _i, _i, _i, _i, _i, _i, _i, c_p, c_p]),
     "rgrg_backbone": (_i, [c_p, c_p, _i, _i, c_p, c_p]),
     "rgrg_debug_read": (_i, [c_p, C.c_char_p, c_p, C.c_size_t]),

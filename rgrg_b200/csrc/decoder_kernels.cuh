@@ -26,6 +26,8 @@ __device__ __forceinline__ float float_from_key_dec(unsigned k) {
 // token of row r at step t = ids[r, t]; position = t.
 __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ wte, const int* __restrict__ ids, int ids_ld,
                                                     const int* __restrict__ step_ptr, float* __restrict__ h) {
+  griddep_wait();
+  griddep_launch_dependents();
   const int r = blockIdx.x;
   const int t = *step_ptr;
   const int tok = ids[static_cast<size_t>(r) * ids_ld + t];
@@ -37,17 +39,34 @@ __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ wt
 }
 
 // K16  LayerNorm(eps 1e-5) over 1024 features: fp32 residual stream -> bf16 GEMM operand.  One warp per row.
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ h, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, bf16* __restrict__ out, int rows) {
+// Fused with the residual update of the GEMM that precedes it (language_model.py:350, :357): when `parts` is given,
+// h <- h + bias + sum of the GEMM's split-K partial sums (written by its epilogue), stored back, then normalised.
+template <int NPARTS>
+__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ h, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, bf16* __restrict__ out, int rows,
+                                                        const float* __restrict__ parts, size_t part_stride,
+                                                        const float* __restrict__ res_bias) {
+  griddep_wait();
+  griddep_launch_dependents();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float4* src = reinterpret_cast<const float4*>(h + static_cast<size_t>(row) * D);
+  float4* src = reinterpret_cast<float4*>(h + static_cast<size_t>(row) * D);
   float v[32];
   float sum = 0.0f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float4 x = src[i * 32 + lane];
+    float4 x = src[i * 32 + lane];
+    if constexpr (NPARTS > 0) {
+      const float4 b = *reinterpret_cast<const float4*>(res_bias + (i * 32 + lane) * 4);
+      x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+#pragma unroll
+      for (int p = 0; p < NPARTS; ++p) {
+        const float4 t = *reinterpret_cast<const float4*>(parts + p * part_stride + static_cast<size_t>(row) * D + (i * 32 + lane) * 4);
+        x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
+      }
+      src[i * 32 + lane] = x;
+    }
     v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
     sum += x.x + x.y + x.z + x.w;
   }
@@ -82,6 +101,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__ q, KvGeom kv, int layer,
                                                         const int* __restrict__ step_ptr, bf16* __restrict__ out, int rows,
                                                         const unsigned char* __restrict__ anc, int anc_ld, int nb) {
+  griddep_wait();
+  griddep_launch_dependents();
   const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (gw >= rows * HEADS) return;
@@ -180,6 +201,7 @@ __global__ void __launch_bounds__(256) greedy_update_kernel(const float* __restr
                                                             int n_tiles, const float* __restrict__ logits /*or null*/,
                                                             GreedyState g, int rows) {
   // one warp per row, 8 rows per CTA; the last CTA to finish publishes step + 1 (all CTAs read the step first)
+  griddep_wait();
   const int t = *g.step_ptr;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;

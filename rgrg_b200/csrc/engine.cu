@@ -169,6 +169,8 @@ struct rgrg_engine {
   int opt_implicit_conv = 1;
   int opt_cuda_graph = 1;
   int opt_gemm_impl = 0;
+  int opt_pdl = 1;
+  bool pdl_now = false;  // set while the decode step is being issued: its kernels carry the PDL launch attribute
   std::unordered_map<std::string, HostRef> host;
   std::vector<void*> weight_allocs;
 
@@ -190,6 +192,7 @@ struct rgrg_engine {
   DevBuf lm_in;
   // ---- workspace (decoder)
   int ws_rows = 0, ws_slots = 0;
+  DevBuf splitk_parts;
   DevBuf kv_cache, h, x, q, attn_o, mlp_mid, a1, img, part_val, part_idx, ids, unfinished, unf_count, step, logits_tmp;
   int last_B = 0, last_S = 0, last_P = 0;
   // beam search: cache-slot ancestry of the current step (null in greedy mode)
@@ -210,7 +213,7 @@ struct rgrg_engine {
                      &prop_scores, &prop_count, &roi_off, &pooled, &f6, &f7, &pred_out, &detected, &top_idx,
                      &top_scores, &top_boxes, &mean2048, &trf, &s0, &s1, &sel_logits, &selected, &sel_rows, &num_sel,
                      &lm_in, &kv_cache, &h, &x, &q, &attn_o, &mlp_mid, &a1, &img, &part_val, &part_idx, &ids,
-                     &unfinished, &unf_count, &step, &logits_tmp, &b_ids2, &b_anc[0], &b_anc[1], &b_scores, &b_cand_score,
+                     &unfinished, &unf_count, &step, &logits_tmp, &splitk_parts, &b_ids2, &b_anc[0], &b_anc[1], &b_scores, &b_cand_score,
                      &b_cand_token, &b_cand_beam, &b_hyp_score, &b_hyp_len, &b_hyp_tok, &b_hyp_count, &b_worst, &b_done, &b_not_done};
     for (DevBuf* b : all) b->release();
   }
@@ -226,6 +229,11 @@ struct rgrg_engine {
   // ================================================================================================================
   // GEMM dispatch
   // ================================================================================================================
+  template <class Epi>
+  void simt_f32(const float* A, const float* Wt, int M, int N, int K, const Epi& ep, cudaStream_t st) {
+    simt::launch<float, float, Epi>(A, Wt, M, N, K, ep, st);
+  }
+
   template <class Epi>
   void gemm(const char* tag, const bf16* A, int M, const Linear& W, const Epi& epi, cudaStream_t st, bool m_fastest,
             int force_bn = 0) {
@@ -255,15 +263,43 @@ struct rgrg_engine {
     ++launches;
   }
 
-  // N-tile width: fewest (waves x per-k-block cycles).  Per k-block a 128 x BN tile costs max(2*BN MMA cycles,
-  // (16 KB + BN*128 B) / 128 B/clk of shared-memory operand reads): narrow tiles are smem-bandwidth bound.
+  // split-K GEMM for the two residual projections of a decoder layer (M = rows is only ~8 tiles tall): partial sums of
+  // slice s go to parts[s] (fp32 [M, N]); the LayerNorm that follows adds them (+ bias) into the residual stream.
+  void gemm_splitk(const char* tag, const bf16* A, int M, const Linear& W, float* parts, int splits, cudaStream_t st) {
+    if (M <= 0) return;
+    ProfScope ps(this, tag, st);
+    auto ep = epi<false, ACT_NONE, RES_NONE, false>(parts, nullptr, W.N);
+    ep.split_stride = static_cast<size_t>(M) * W.N;
+    if (opt_gemm_impl == 2) {  // CUDA-core cross-check: one full-K pass into slice 0, zeros elsewhere
+      CUDA_CHECK(cudaMemsetAsync(parts, 0, static_cast<size_t>(splits) * M * W.N * 4, st));
+      simt::launch<bf16, bf16, decltype(ep)>(A, W.w, M, W.N, W.K, ep, st);
+      ++launches;
+      return;
+    }
+    tc::GemmShape s{};
+    s.M = M;
+    s.N = W.N;
+    s.k_iters = W.K / 64;
+    s.k_splits = splits;
+    s.m_tiles = ceil_div(M, tc::BM);
+    s.n_tiles = ceil_div(W.N, 256);
+    s.m_fastest = 1;
+    if (s.k_iters % splits) throw std::runtime_error("split-K factor must divide K / 64");
+    CUtensorMap tmA = tc::make_tmap_2d(A, M, W.K, 128);
+    launch_bn(256, tmA, W, s, ep, st);
+    ++launches;
+  }
+
+  // N-tile width: fewest waves x per-k-block cycles.  Measured on B200 (profiles/r01_v2_gemm_timeline.md): a
+  // 128 x N x 16 tcgen05.mma occupies the tensor pipe ~128 cycles for every N in {64..256}, so a k-block costs
+  // ~520 cycles regardless of the tile width and narrow tiles only help by shortening the tail wave.
   static int pick_bn(int m_tiles, int N) {
     int best = 128;
     long long best_cost = -1;
     for (int bn = 64; bn <= 256; bn += 64) {
       const long long tiles = static_cast<long long>(m_tiles) * ceil_div(N, bn);
       const long long waves = (tiles + tc::num_sms() - 1) / tc::num_sms();
-      const long long cyc = std::max<long long>(2 * bn, (16384 + bn * 128) / 128);
+      const long long cyc = 520 + bn / 2;             // + epilogue share, which grows with the tile
       const long long cost = waves * (cyc * 16 + 600);  // + fixed per-tile overhead (pipeline fill / drain)
       if (best_cost < 0 || cost <= best_cost) {
         best_cost = cost;
@@ -275,10 +311,10 @@ struct rgrg_engine {
   template <class Epi>
   void launch_bn(int bn, const CUtensorMap& tmA, const Linear& W, const tc::GemmShape& s, const Epi& epi, cudaStream_t st) {
     switch (bn) {
-      case 64: tc::launch<64, 8, Epi>(tmA, W.tm[0], s, epi, st); break;
-      case 128: tc::launch<128, 6, Epi>(tmA, W.tm[1], s, epi, st); break;
-      case 192: tc::launch<192, 5, Epi>(tmA, W.tm[2], s, epi, st); break;
-      case 256: tc::launch<256, 4, Epi>(tmA, W.tm[3], s, epi, st); break;
+      case 64: tc::launch<64, 8, Epi>(tmA, W.tm[0], s, epi, st, pdl_now); break;
+      case 128: tc::launch<128, 6, Epi>(tmA, W.tm[1], s, epi, st, pdl_now); break;
+      case 192: tc::launch<192, 5, Epi>(tmA, W.tm[2], s, epi, st, pdl_now); break;
+      case 256: tc::launch<256, 4, Epi>(tmA, W.tm[3], s, epi, st, pdl_now); break;
       default: throw std::runtime_error("unsupported N tile");
     }
   }
@@ -331,22 +367,14 @@ struct rgrg_engine {
     }
   }
 
-  static EpiStore store_bf16(bf16* out, const float* bias, int ldc, int act, const bf16* res = nullptr) {
-    EpiStore e{};
-    e.out_bf16 = out;
+  template <bool OUT_BF16, int ACT, int RES, bool BIAS>
+  static EpiStoreT<OUT_BF16, ACT, RES, BIAS> epi(void* out, const float* bias, int ldc, const void* res = nullptr) {
+    EpiStoreT<OUT_BF16, ACT, RES, BIAS> e{};
+    e.out = out;
     e.bias = bias;
+    e.res = res;
     e.ldc = ldc;
-    e.act = act;
-    e.res_bf16 = res;
-    return e;
-  }
-  static EpiStore store_f32(float* out, const float* bias, int ldc, int act, const float* res = nullptr) {
-    EpiStore e{};
-    e.out_f32 = out;
-    e.bias = bias;
-    e.ldc = ldc;
-    e.act = act;
-    e.res_f32 = res;
+    e.split_stride = 0;
     return e;
   }
 
@@ -690,9 +718,9 @@ struct rgrg_engine {
       const int Ho = H / bw.stride;
       const int M_in = B * H * H, M_out = B * Ho * Ho;
       // conv1 1x1 + BN + ReLU
-      gemm("conv1x1", xin, M_in, bw.c1, store_bf16(t1.as<bf16>(), bw.c1.bias, bw.width, ACT_RELU), st, false);
+      gemm("conv1x1", xin, M_in, bw.c1, epi<true, ACT_RELU, RES_NONE, true>(t1.p, bw.c1.bias, bw.width), st, false);
       // conv2 3x3 (stride here, v1.5) + BN + ReLU
-      conv3x3("conv3x3", t1.as<bf16>(), B, H, H, bw.width, bw.stride, bw.c2, store_bf16(t2.as<bf16>(), bw.c2.bias, bw.width, ACT_RELU), st);
+      conv3x3("conv3x3", t1.as<bf16>(), B, H, H, bw.width, bw.stride, bw.c2, epi<true, ACT_RELU, RES_NONE, true>(t2.p, bw.c2.bias, bw.width), st);
       // identity / downsample branch
       const bf16* identity = xin;
       if (bw.has_ds) {
@@ -706,11 +734,11 @@ struct rgrg_engine {
           ++launches;
           ds_in = sub.as<bf16>();
         }
-        gemm("conv1x1", ds_in, M_out, bw.ds, store_bf16(idb.as<bf16>(), bw.ds.bias, bw.cout, ACT_NONE), st, false);
+        gemm("conv1x1", ds_in, M_out, bw.ds, epi<true, ACT_NONE, RES_NONE, true>(idb.p, bw.ds.bias, bw.cout), st, false);
         identity = idb.as<bf16>();
       }
       // conv3 1x1 + BN, + identity, ReLU
-      gemm("conv1x1", t2.as<bf16>(), M_out, bw.c3, store_bf16(yout, bw.c3.bias, bw.cout, ACT_RELU, identity), st, false);
+      gemm("conv1x1", t2.as<bf16>(), M_out, bw.c3, epi<true, ACT_RELU, RES_BF16, true>(yout, bw.c3.bias, bw.cout, identity), st, false);
       cur ^= 1;
       H = Ho;
     }
@@ -729,8 +757,8 @@ struct rgrg_engine {
     const int f = S / 32;
     run_backbone(img_dev, B, S, feats.as<bf16>(), st);
     // RPN head: 3x3 conv + ReLU, then both 1x1 heads as one N = 160 + 640 GEMM with fp32 (decision-critical) output
-    conv3x3("rpn_conv", feats.as<bf16>(), B, f, f, 2048, 1, rpn_conv, store_bf16(rpn_t.as<bf16>(), rpn_conv.bias, 2048, ACT_RELU), st);
-    gemm("rpn_heads", rpn_t.as<bf16>(), B * f * f, rpn_heads, store_f32(rpn_out.as<float>(), rpn_heads.bias, 800, ACT_NONE), st, false);
+    conv3x3("rpn_conv", feats.as<bf16>(), B, f, f, 2048, 1, rpn_conv, epi<true, ACT_RELU, RES_NONE, true>(rpn_t.p, rpn_conv.bias, 2048), st);
+    gemm("rpn_heads", rpn_t.as<bf16>(), B * f * f, rpn_heads, epi<false, ACT_NONE, RES_NONE, true>(rpn_out.p, rpn_heads.bias, 800), st, false);
     det::RpnIn in{};
     in.obj = rpn_out.as<float>();
     in.deltas = rpn_out.as<float>() + 160;
@@ -758,9 +786,9 @@ struct rgrg_engine {
         KERNEL_CHECK();
         ++launches;
       }
-      gemm("fc6", pooled.as<bf16>(), P_total, fc6, store_bf16(f6.as<bf16>(), fc6.bias, 1024, ACT_RELU), st, false);
-      gemm("fc7", f6.as<bf16>(), P_total, fc7, store_bf16(f7.as<bf16>(), fc7.bias, 1024, ACT_RELU), st, true);
-      gemm("box_predictor", f7.as<bf16>(), P_total, pred, store_f32(pred_out.as<float>(), pred.bias, 150, ACT_NONE), st, true);
+      gemm("fc6", pooled.as<bf16>(), P_total, fc6, epi<true, ACT_RELU, RES_NONE, true>(f6.p, fc6.bias, 1024), st, false);
+      gemm("fc7", f6.as<bf16>(), P_total, fc7, epi<true, ACT_RELU, RES_NONE, true>(f7.p, fc7.bias, 1024), st, true);
+      gemm("box_predictor", f7.as<bf16>(), P_total, pred, epi<false, ACT_NONE, RES_NONE, true>(pred_out.p, pred.bias, 150), st, true);
     }
     ProfScope ps_tail(this, "region_tail", st);
     det::RoiTailOut to{detected.as<uint8_t>(), top_idx.as<int>(), top_scores.as<float>(), top_boxes.as<float>()};
@@ -773,10 +801,10 @@ struct rgrg_engine {
     launches += 2;
     const int rows = B * NREG;
     // dim_reduction + selection MLP in fp32 on CUDA cores (decision-critical, 0.01 % of the FLOPs)
-    simt::launch<float, float, EpiStore>(mean2048.as<float>(), dimred.w, rows, 1024, 2048,
-                                         store_f32(trf.as<float>(), dimred.bias, 1024, ACT_NONE), st);
-    simt::launch<float, float, EpiStore>(trf.as<float>(), sel0.w, rows, 512, 1024, store_f32(s0.as<float>(), sel0.bias, 512, ACT_RELU), st);
-    simt::launch<float, float, EpiStore>(s0.as<float>(), sel2.w, rows, 128, 512, store_f32(s1.as<float>(), sel2.bias, 128, ACT_RELU), st);
+    simt_f32(mean2048.as<float>(), dimred.w, rows, 1024, 2048,
+             epi<false, ACT_NONE, RES_NONE, true>(trf.p, dimred.bias, 1024), st);
+    simt_f32(trf.as<float>(), sel0.w, rows, 512, 1024, epi<false, ACT_RELU, RES_NONE, true>(s0.p, sel0.bias, 512), st);
+    simt_f32(s0.as<float>(), sel2.w, rows, 128, 512, epi<false, ACT_RELU, RES_NONE, true>(s1.p, sel2.bias, 128), st);
     det::selection_tail_kernel<<<1, 1024, 0, st>>>(s1.as<float>(), sel4.w, sel4.bias, detected.as<uint8_t>(), sel_logits.as<float>(),
                                                    selected.as<uint8_t>(), sel_rows.as<int>(), num_sel.as<int>(), rows);
     KERNEL_CHECK();
@@ -805,10 +833,11 @@ struct rgrg_engine {
       q.ensure(rr * DM * 2);
       attn_o.ensure(rr * DM * 2);
       mlp_mid.ensure(rr * 4 * DM * 2);
+      splitk_parts.ensure(rr * DM * 4 * 4);
       a1.ensure(rr * DM * 2);
       img.ensure(rr * DM * 2);
-      part_val.ensure(rr * 1024 * 4);
-      part_idx.ensure(rr * 1024 * 4);
+      part_val.ensure(rr * 2048 * 4);
+      part_idx.ensure(rr * 2048 * 4);
       ids.ensure(rr * (s + 1) * 4);
       unfinished.ensure(rr * 4);
       unf_count.ensure(static_cast<size_t>(s + 1) * 4);
@@ -824,8 +853,8 @@ struct rgrg_engine {
 
   // language_model.py:284 (once instead of every step) + :140-147 for all 24 layers in one GEMM
   void lm_prologue(const bf16* feats_bf16, int R, int beams, cudaStream_t st) {
-    gemm("lm_prologue", feats_bf16, R, fst0, store_bf16(a1.as<bf16>(), fst0.bias, DM, ACT_RELU), st, true);
-    gemm("lm_prologue", a1.as<bf16>(), R, fst2, store_bf16(img.as<bf16>(), fst2.bias, DM, ACT_NONE), st, true);
+    gemm("lm_prologue", feats_bf16, R, fst0, epi<true, ACT_RELU, RES_NONE, true>(a1.p, fst0.bias, DM), st, true);
+    gemm("lm_prologue", a1.as<bf16>(), R, fst2, epi<true, ACT_NONE, RES_NONE, true>(img.p, fst2.bias, DM), st, true);
     EpiImageKv e{ukv.bias, kv_geom(), beams};
     gemm("lm_image_kv", img.as<bf16>(), R, ukv, e, st, true);
   }
@@ -836,43 +865,48 @@ struct rgrg_engine {
     const int* sp = step.as<int>();
     {
       ProfScope ps(this, "embed", st);
-      dec::embed_kernel<<<rows, 256, 0, st>>>(wte_f32, ids_ptr, ids_ld, sp, h.as<float>());
-      KERNEL_CHECK();
+      launch_kernel(dec::embed_kernel, dim3(rows), dim3(256), 0, st, false, wte_f32, ids_ptr, ids_ld, sp, h.as<float>());
       ++launches;
     }
+    pdl_now = opt_pdl != 0;
     const int ln_grid = ceil_div(rows, 8);
+    constexpr int SPLITS = 4;
+    const size_t pstride = static_cast<size_t>(rows) * DM;
+    float* parts = splitk_parts.as<float>();
+    // LayerNorm fused with the residual update of the preceding split-K projection (pending_bias != null)
+    const float* pending_bias = nullptr;
+    auto ln = [&](const float* g, const float* b) {
+      ProfScope ps(this, "layernorm", st);
+      if (pending_bias)
+        launch_kernel(dec::layernorm_kernel<SPLITS>, dim3(ln_grid), dim3(256), 0, st, pdl_now, h.as<float>(), g, b, x.as<bf16>(), rows,
+                      parts, pstride, pending_bias);
+      else
+        launch_kernel(dec::layernorm_kernel<0>, dim3(ln_grid), dim3(256), 0, st, pdl_now, h.as<float>(), g, b, x.as<bf16>(), rows,
+                      parts, pstride, pending_bias);
+      ++launches;
+      pending_bias = nullptr;
+    };
     for (int l = 0; l < NLAYER; ++l) {
       const LayerW& L = layers[l];
-      {
-        ProfScope ps(this, "layernorm", st);
-        dec::layernorm_kernel<<<ln_grid, 256, 0, st>>>(h.as<float>(), L.ln1_g, L.ln1_b, x.as<bf16>(), rows);
-        KERNEL_CHECK();
-      }
+      ln(L.ln1_g, L.ln1_b);
       EpiQkvAppend eq{q.as<bf16>(), L.attn.bias, kv_geom(), l, sp};
       gemm("c_attn", x.as<bf16>(), rows, L.attn, eq, st, true);
       {
         ProfScope ps(this, "attention", st);
-        dec::attention_kernel<<<ceil_div(rows * 16, 4), 128, 0, st>>>(q.as<bf16>(), kv_geom(), l, sp, attn_o.as<bf16>(), rows,
-                                                                      beam_anc, beam_slots, beam_nb);
-        KERNEL_CHECK();
+        launch_kernel(dec::attention_kernel, dim3(ceil_div(rows * 16, 4)), dim3(128), 0, st, pdl_now, q.as<bf16>(), kv_geom(), l, sp,
+                      attn_o.as<bf16>(), rows, beam_anc, beam_slots, beam_nb);
+        ++launches;
       }
-      gemm("attn_c_proj", attn_o.as<bf16>(), rows, L.proj, store_f32(h.as<float>(), L.proj.bias, DM, ACT_NONE, h.as<float>()), st, true);
-      {
-        ProfScope ps(this, "layernorm", st);
-        dec::layernorm_kernel<<<ln_grid, 256, 0, st>>>(h.as<float>(), L.ln2_g, L.ln2_b, x.as<bf16>(), rows);
-        KERNEL_CHECK();
-      }
-      gemm("mlp_c_fc", x.as<bf16>(), rows, L.fc, store_bf16(mlp_mid.as<bf16>(), L.fc.bias, 4 * DM, ACT_GELU_NEW), st, true);
-      gemm("mlp_c_proj", mlp_mid.as<bf16>(), rows, L.mproj, store_f32(h.as<float>(), L.mproj.bias, DM, ACT_NONE, h.as<float>()), st, true);
-      launches += 3;
+      gemm_splitk("attn_c_proj", attn_o.as<bf16>(), rows, L.proj, parts, SPLITS, st);
+      pending_bias = L.proj.bias;
+      ln(L.ln2_g, L.ln2_b);
+      gemm("mlp_c_fc", x.as<bf16>(), rows, L.fc, epi<true, ACT_GELU_NEW, RES_NONE, true>(mlp_mid.p, L.fc.bias, 4 * DM), st, true);
+      gemm_splitk("mlp_c_proj", mlp_mid.as<bf16>(), rows, L.mproj, parts, SPLITS, st);
+      pending_bias = L.mproj.bias;
     }
-    {
-      ProfScope ps(this, "layernorm", st);
-      dec::layernorm_kernel<<<ln_grid, 256, 0, st>>>(h.as<float>(), lnf_g, lnf_b, x.as<bf16>(), rows);
-      KERNEL_CHECK();
-      ++launches;
-    }
+    ln(lnf_g, lnf_b);
   }
+  void end_pdl() { pdl_now = false; }
 
   // one greedy decode step.  logits_out != null: lm_head stores fp32 logits there instead of the fused arg-max.
   int decode_step(int rows, const dec::GreedyState& g, float* logits_out, cudaStream_t st) {
@@ -880,18 +914,21 @@ struct rgrg_engine {
     decode_forward(rows, g.ids, g.ids_ld, st);
     if (logits_out || opt_gemm_impl == 2) {
       float* dst = logits_out ? logits_out : logits_tmp.as<float>();
-      gemm("lm_head", x.as<bf16>(), rows, lm_head, store_f32(dst, nullptr, VOCAB, ACT_NONE), st, true);
+      gemm("lm_head", x.as<bf16>(), rows, lm_head, epi<false, ACT_NONE, RES_NONE, false>(dst, nullptr, VOCAB), st, true);
       ProfScope ps(this, "greedy_update", st);
-      dec::greedy_update_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(nullptr, nullptr, 0, dst, g, rows);
+      launch_kernel(dec::greedy_update_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, st, pdl_now, static_cast<const float*>(nullptr),
+                    static_cast<const int*>(nullptr), 0, static_cast<const float*>(dst), g, rows);
     } else {
       const int bn = pick_bn(ceil_div(rows, tc::BM), VOCAB);
-      const int n_tiles = ceil_div(VOCAB, bn);
+      const int n_tiles = 2 * ceil_div(VOCAB, bn);  // two partials per tile: one per epilogue warp of a lane quarter
       EpiArgmaxPartial ea{part_val.as<float>(), part_idx.as<int>(), n_tiles};
       gemm("lm_head", x.as<bf16>(), rows, lm_head, ea, st, true, bn);
       ProfScope ps(this, "greedy_update", st);
-      dec::greedy_update_kernel<<<ceil_div(rows, 8), 256, 0, st>>>(part_val.as<float>(), part_idx.as<int>(), n_tiles, nullptr, g, rows);
+      launch_kernel(dec::greedy_update_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, st, pdl_now,
+                    static_cast<const float*>(part_val.as<float>()), static_cast<const int*>(part_idx.as<int>()), n_tiles,
+                    static_cast<const float*>(nullptr), g, rows);
     }
-    KERNEL_CHECK();
+    end_pdl();
     ++launches;
     return static_cast<int>(launches) - before;
   }
@@ -1038,7 +1075,8 @@ struct rgrg_engine {
     for (int t = 0; t < steps; ++t) {
       beam_anc = s.anc[cur];
       decode_forward(rows, s.ids[cur], max_length, st);
-      gemm("lm_head", x.as<bf16>(), rows, lm_head, store_f32(logits_tmp.as<float>(), nullptr, VOCAB, ACT_NONE), st, true);
+      gemm("lm_head", x.as<bf16>(), rows, lm_head, epi<false, ACT_NONE, RES_NONE, false>(logits_tmp.p, nullptr, VOCAB), st, true);
+      end_pdl();
       beam_bookkeeping(s, logits_tmp.as<float>(), R, cur, st);
       cur ^= 1;
       ++done_steps;
@@ -1233,6 +1271,7 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   if (k == "implicit_conv") e->opt_implicit_conv = value;
   else if (k == "cuda_graph") e->opt_cuda_graph = value;
   else if (k == "gemm_impl") e->opt_gemm_impl = value;
+  else if (k == "pdl") e->opt_pdl = value;
   else {
     e->err = "unknown option: " + k;
     return 1;
@@ -1451,19 +1490,85 @@ int rgrg_gemm_bf16(rgrg_engine_t* e, const void* A_dev, const void* W_dev, const
     L.bias = const_cast<float*>(bias_dev);
     L.N = N;
     L.K = K;
-    EpiStore ep = rgrg_engine::store_f32(out_dev, bias_dev, N, act);
     const int saved = e->opt_gemm_impl;
     e->opt_gemm_impl = impl == 2 ? 2 : 0;
+    const int fbn = impl == 0 ? 128 : impl == 1 ? 64 : impl == 3 ? 192 : impl == 4 ? 256 : 0;
+    const bf16* A = static_cast<const bf16*>(A_dev);
     try {
       if (impl != 2) L.make_maps();
-      e->gemm("test_gemm", static_cast<const bf16*>(A_dev), M, L, ep, st, true,
-              impl == 0 ? 128 : impl == 1 ? 64 : impl == 3 ? 192 : impl == 4 ? 256 : 0);
+      if (bias_dev) {
+        if (act == ACT_RELU) e->gemm("test_gemm", A, M, L, rgrg_engine::epi<false, ACT_RELU, RES_NONE, true>(out_dev, bias_dev, N), st, true, fbn);
+        else if (act == ACT_GELU_NEW) e->gemm("test_gemm", A, M, L, rgrg_engine::epi<false, ACT_GELU_NEW, RES_NONE, true>(out_dev, bias_dev, N), st, true, fbn);
+        else e->gemm("test_gemm", A, M, L, rgrg_engine::epi<false, ACT_NONE, RES_NONE, true>(out_dev, bias_dev, N), st, true, fbn);
+      } else {
+        if (act == ACT_RELU) e->gemm("test_gemm", A, M, L, rgrg_engine::epi<false, ACT_RELU, RES_NONE, false>(out_dev, nullptr, N), st, true, fbn);
+        else if (act == ACT_GELU_NEW) e->gemm("test_gemm", A, M, L, rgrg_engine::epi<false, ACT_GELU_NEW, RES_NONE, false>(out_dev, nullptr, N), st, true, fbn);
+        else e->gemm("test_gemm", A, M, L, rgrg_engine::epi<false, ACT_NONE, RES_NONE, false>(out_dev, nullptr, N), st, true, fbn);
+      }
     } catch (...) {
       e->opt_gemm_impl = saved;
       throw;
     }
     e->opt_gemm_impl = saved;
     CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+// tuning harness: `iters` back-to-back launches of one GEMM on the engine stream (no host sync in between), optionally
+// interleaved with a LayerNorm launch; returns the average time per iteration and the last launch's CTA timeline
+int rgrg_gemm_bench(rgrg_engine_t* e, int M, int N, int K, int bn, int iters, int interleave, float* out_ms,
+                    long long* trace_host, int trace_ctas) {
+  RGRG_TRY(e, {
+    cudaStream_t st = e->enter(nullptr);
+    DevBuf A, W, O, H, G, T;
+    A.ensure(static_cast<size_t>(M) * K * 2);
+    W.ensure(static_cast<size_t>(N) * K * 2);
+    O.ensure(static_cast<size_t>(M) * N * 2);
+    H.ensure(static_cast<size_t>(M) * 1024 * 4);
+    G.ensure(1024 * 4);
+    T.ensure(static_cast<size_t>(160) * 8 * 8);
+    CUDA_CHECK(cudaMemsetAsync(A.p, 0, A.bytes, st));
+    CUDA_CHECK(cudaMemsetAsync(W.p, 0, W.bytes, st));
+    CUDA_CHECK(cudaMemsetAsync(H.p, 0, H.bytes, st));
+    CUDA_CHECK(cudaMemsetAsync(G.p, 0, G.bytes, st));
+    CUDA_CHECK(cudaMemsetAsync(T.p, 0, T.bytes, st));
+    Linear L;
+    L.w = W.as<bf16>();
+    L.N = N;
+    L.K = K;
+    L.make_maps();
+    auto ep = rgrg_engine::epi<true, ACT_NONE, RES_NONE, false>(O.p, nullptr, N);
+    tc::GemmShape s{};
+    s.M = M;
+    s.N = N;
+    s.k_iters = K / 64;
+    s.m_tiles = ceil_div(M, 128);
+    s.n_tiles = ceil_div(N, bn);
+    s.m_fastest = 1;
+    CUtensorMap tmA = tc::make_tmap_2d(A.as<bf16>(), M, K, 128);
+    cudaEvent_t a;
+    cudaEvent_t b;
+    CUDA_CHECK(cudaEventCreate(&a));
+    CUDA_CHECK(cudaEventCreate(&b));
+    for (int rep = 0; rep < 2; ++rep) {  // rep 0 = warm-up
+      if (rep == 1) CUDA_CHECK(cudaEventRecord(a, st));
+      for (int i = 0; i < iters; ++i) {
+        s.trace = (rep == 1 && i == iters - 1) ? T.as<long long>() : nullptr;
+        e->launch_bn(bn, tmA, L, s, ep, st);
+        if (interleave)
+          dec::layernorm_kernel<0><<<ceil_div(M, 8), 256, 0, st>>>(H.as<float>(), G.as<float>(), G.as<float>(), A.as<bf16>(), M, nullptr, 0,
+                                                                  nullptr);
+      }
+      if (rep == 1) CUDA_CHECK(cudaEventRecord(b, st));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+    *out_ms = ms / iters;
+    if (trace_host) CUDA_CHECK(cudaMemcpy(trace_host, T.p, static_cast<size_t>(trace_ctas) * 64, cudaMemcpyDeviceToHost));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    A.release(); W.release(); O.release(); H.release(); G.release(); T.release();
   });
 }
 
@@ -1477,11 +1582,12 @@ int rgrg_conv3x3_bf16(rgrg_engine_t* e, const void* in_dev, const void* w_dev, c
     L.N = Cout;
     L.K = 9 * Cin;
     L.make_maps();
-    EpiStore ep = rgrg_engine::store_f32(out_dev, bias_dev, Cout, relu ? ACT_RELU : ACT_NONE);
+    if (!bias_dev) throw std::runtime_error("conv test entry needs a bias");
     const int saved = e->opt_implicit_conv;
     e->opt_implicit_conv = implicit;
     try {
-      e->conv3x3("test_conv", static_cast<const bf16*>(in_dev), B, H, W, Cin, 1, L, ep, st);
+      if (relu) e->conv3x3("test_conv", static_cast<const bf16*>(in_dev), B, H, W, Cin, 1, L, rgrg_engine::epi<false, ACT_RELU, RES_NONE, true>(out_dev, bias_dev, Cout), st);
+      else e->conv3x3("test_conv", static_cast<const bf16*>(in_dev), B, H, W, Cin, 1, L, rgrg_engine::epi<false, ACT_NONE, RES_NONE, true>(out_dev, bias_dev, Cout), st);
     } catch (...) {
       e->opt_implicit_conv = saved;
       throw;

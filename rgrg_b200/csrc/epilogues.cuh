@@ -1,69 +1,109 @@
 // Fused GEMM epilogues.  A functor sees one output row and NV consecutive accumulator columns at a time:
-//   init(State&)                                   once per thread and tile
+//   init(State&, split)                               once per thread and tile (split = split-K slice of the tile)
 //   apply<NV>(State&, row, col0, const float* v, N)   v[j] = D[row, col0 + j]; columns >= N are padding
-//   finish(State&, row, n_blk)                     kDirect functors only: once per row after the tile's last chunk
-// The tcgen05 kernel calls apply<8> after its shared-memory transpose (a lane owns 8 consecutive columns, 4 lanes cover
-// a 128-byte fp32 row segment) or, for kDirect functors (reductions along N), apply<32> with one row per thread;
-// the CUDA-core kernel calls apply<4>.
+//   finish(State&, row, part)                         kDirect functors only: once per row after the thread's last chunk
+// The tcgen05 kernel calls apply<8> after its shared-memory transpose (a lane owns 8 consecutive columns of a row, so
+// global accesses are 16-byte vectors, 2 lanes per 64-byte bf16 / 4 lanes per 128-byte fp32 segment) or, for kDirect
+// functors (reductions along N), apply<16> with one row per thread; the CUDA-core kernel calls apply<4>.
+// Everything that selects behaviour is a template parameter: the hot loop carries no runtime branches on options.
 #pragma once
 #include "common.cuh"
 
 namespace rgrg {
 
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU_NEW = 2 };
+enum Res { RES_NONE = 0, RES_BF16 = 1, RES_F32 = 2 };
 
-// out = act(acc + bias [+ residual]); bf16 or fp32 destination; residual bf16 (bottleneck identity) or fp32
-// (decoder residual stream; out_f32 may alias res_f32 — each element is read then written by the same thread).
-struct EpiStore {
-  struct State {};
+template <int NV>
+__device__ __forceinline__ void add_vec_f32(float* o, const float* __restrict__ src) {
+  if constexpr (NV % 4 == 0) {
+#pragma unroll
+    for (int j = 0; j < NV; j += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(src + j);
+      o[j] += t.x; o[j + 1] += t.y; o[j + 2] += t.z; o[j + 3] += t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) o[j] += src[j];
+  }
+}
+
+// out = act(acc + bias [+ residual]) -> bf16 or fp32.  Residual: bf16 (bottleneck identity) or fp32 (decoder residual
+// stream; `out` may alias `res` — each element is read then written by the same thread).
+template <bool OUT_BF16, int ACT, int RES, bool BIAS>
+struct EpiStoreT {
+  struct State {
+    size_t split_off;
+  };
   static constexpr bool kDirect = false;
-  float* out_f32;
-  bf16* out_bf16;
-  const float* bias;     // [N] or null
-  const bf16* res_bf16;  // [M, ldc] or null
-  const float* res_f32;  // [M, ldc] or null
+  void* out;            // bf16* or float*
+  const float* bias;    // [N]
+  const void* res;      // bf16* or float*, [M, ldc]
   int ldc;
-  int act;
+  size_t split_stride;  // split-K: slice s of the partial sums goes to out + s * split_stride (elements); 0 otherwise
 
-  __device__ __forceinline__ void init(State&) const {}
+  __device__ __forceinline__ void init(State& s, int split) const { s.split_off = split * split_stride; }
   __device__ __forceinline__ void finish(State&, int, int) const {}
 
   template <int NV>
-  __device__ __forceinline__ void apply(State&, int row, int col0, const float* v, int N) const {
-    const size_t base = static_cast<size_t>(row) * ldc + col0;
-    const bool full = (col0 + NV <= N);
+  __device__ __forceinline__ void apply(State& st, int row, int col0, const float* v, int N) const {
+    const size_t base = static_cast<size_t>(row) * ldc + col0 + st.split_off;
     float o[NV];
 #pragma unroll
+    for (int j = 0; j < NV; ++j) o[j] = v[j];
+    const bool full = (col0 + NV <= N);
+    const bool vec = full && ((ldc & 7) == 0);  // row starts stay 16-byte aligned for both fp32 and bf16
+    if (vec) {
+      if constexpr (BIAS) add_vec_f32<NV>(o, bias + col0);
+      if constexpr (RES == RES_F32) add_vec_f32<NV>(o, static_cast<const float*>(res) + base);
+      if constexpr (RES == RES_BF16) {
+        if constexpr (NV % 8 == 0) {
+#pragma unroll
+          for (int j = 0; j < NV; j += 8) {
+            float r[8];
+            unpack8(*reinterpret_cast<const uint4*>(static_cast<const bf16*>(res) + base + j), r);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) o[j + k] += r[k];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NV; ++j) o[j] += bf2f(static_cast<const bf16*>(res)[base + j]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        if (col0 + j < N) {
+          if constexpr (BIAS) o[j] += bias[col0 + j];
+          if constexpr (RES == RES_F32) o[j] += static_cast<const float*>(res)[base + j];
+          if constexpr (RES == RES_BF16) o[j] += bf2f(static_cast<const bf16*>(res)[base + j]);
+        }
+      }
+    }
+#pragma unroll
     for (int j = 0; j < NV; ++j) {
-      float x = v[j];
-      if (full || col0 + j < N) {
-        if (bias) x += bias[col0 + j];
-        if (res_bf16) x += bf2f(res_bf16[base + j]);
-        if (res_f32) x += res_f32[base + j];
-      }
-      if (act == ACT_RELU) x = fmaxf(x, 0.0f);
-      else if (act == ACT_GELU_NEW) x = gelu_new(x);
-      o[j] = x;
+      if constexpr (ACT == ACT_RELU) o[j] = fmaxf(o[j], 0.0f);
+      if constexpr (ACT == ACT_GELU_NEW) o[j] = gelu_new(o[j]);
     }
-    if (out_bf16) {
-      if (full && NV % 8 == 0 && (ldc & 7) == 0) {
+    if constexpr (OUT_BF16) {
+      bf16* dst = static_cast<bf16*>(out) + base;
+      if (vec && NV % 8 == 0) {
 #pragma unroll
-        for (int j = 0; j < NV; j += 8) *reinterpret_cast<uint4*>(out_bf16 + base + j) = pack8(o + j);
+        for (int j = 0; j < NV; j += 8) *reinterpret_cast<uint4*>(dst + j) = pack8(o + j);
       } else {
 #pragma unroll
         for (int j = 0; j < NV; ++j)
-          if (col0 + j < N) out_bf16[base + j] = f2bf(o[j]);
+          if (col0 + j < N) dst[j] = f2bf(o[j]);
       }
-    }
-    if (out_f32) {
-      if (full && NV % 4 == 0 && (ldc & 3) == 0) {
+    } else {
+      float* dst = static_cast<float*>(out) + base;
+      if (vec && NV % 4 == 0) {
 #pragma unroll
-        for (int j = 0; j < NV; j += 4)
-          *reinterpret_cast<float4*>(out_f32 + base + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        for (int j = 0; j < NV; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
       } else {
 #pragma unroll
         for (int j = 0; j < NV; ++j)
-          if (col0 + j < N) out_f32[base + j] = o[j];
+          if (col0 + j < N) dst[j] = o[j];
       }
     }
   }
@@ -79,10 +119,23 @@ struct KvGeom {
   }
 };
 
+template <int NV>
+__device__ __forceinline__ void store_bf16_vec(bf16* dst, const float* o) {
+  if constexpr (NV % 8 == 0) {
+#pragma unroll
+    for (int j = 0; j < NV; j += 8) *reinterpret_cast<uint4*>(dst + j) = pack8(o + j);
+  } else {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) dst[j] = f2bf(o[j]);
+  }
+}
+
 // c_attn epilogue (language_model.py:132 + :169-170 without the torch.cat): columns [0,1024) -> q buffer,
 // [1024,2048) -> K cache, [2048,3072) -> V cache, appended in place at slot *step_ptr + 1.
 struct EpiQkvAppend {
-  struct State {};
+  struct State {
+    int slot;
+  };
   static constexpr bool kDirect = false;
   bf16* q_out;        // [M, 1024]
   const float* bias;  // [3072]
@@ -90,31 +143,23 @@ struct EpiQkvAppend {
   int layer;
   const int* step_ptr;  // device-side decode step t (word t is cached at slot t + 1)
 
-  __device__ __forceinline__ void init(State&) const {}
+  __device__ __forceinline__ void init(State& s, int) const { s.slot = *step_ptr + 1; }
   __device__ __forceinline__ void finish(State&, int, int) const {}
 
   template <int NV>
-  __device__ __forceinline__ void apply(State&, int row, int col0, const float* v, int N) const {
+  __device__ __forceinline__ void apply(State& s, int row, int col0, const float* v, int N) const {
     float o[NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) o[j] = v[j] + bias[col0 + j];
+    for (int j = 0; j < NV; ++j) o[j] = v[j];
+    add_vec_f32<NV>(o, bias + col0);
     bf16* dst;
     if (col0 < 1024) {
       dst = q_out + static_cast<size_t>(row) * 1024 + col0;
     } else {
       const int c = col0 - 1024;
-      const int which = c >> 10;  // 0 = K, 1 = V
-      const int head = (c & 1023) >> 6;
-      const int d0 = c & 63;
-      dst = kv.cache + kv.offset(layer, which, row, head, *step_ptr + 1) + d0;
+      dst = kv.cache + kv.offset(layer, c >> 10, row, (c & 1023) >> 6, s.slot) + (c & 63);
     }
-    if (NV % 8 == 0) {
-#pragma unroll
-      for (int j = 0; j < NV; j += 8) *reinterpret_cast<uint4*>(dst + j) = pack8(o + j);
-    } else {
-#pragma unroll
-      for (int j = 0; j < NV; ++j) dst[j] = f2bf(o[j]);
-    }
+    store_bf16_vec<NV>(dst, o);
   }
 };
 
@@ -127,44 +172,33 @@ struct EpiImageKv {
   KvGeom kv;
   int beams;
 
-  __device__ __forceinline__ void init(State&) const {}
+  __device__ __forceinline__ void init(State&, int) const {}
   __device__ __forceinline__ void finish(State&, int, int) const {}
 
   template <int NV>
   __device__ __forceinline__ void apply(State&, int row, int col0, const float* v, int N) const {
     float o[NV];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) o[j] = v[j] + bias[col0 + j];
-    const int layer = col0 >> 11;
-    const int which = (col0 >> 10) & 1;
-    const int head = (col0 & 1023) >> 6;
-    const int d0 = col0 & 63;
-    for (int b = 0; b < beams; ++b) {
-      bf16* dst = kv.cache + kv.offset(layer, which, row * beams + b, head, 0) + d0;
-      if (NV % 8 == 0) {
-#pragma unroll
-        for (int j = 0; j < NV; j += 8) *reinterpret_cast<uint4*>(dst + j) = pack8(o + j);
-      } else {
-#pragma unroll
-        for (int j = 0; j < NV; ++j) dst[j] = f2bf(o[j]);
-      }
-    }
+    for (int j = 0; j < NV; ++j) o[j] = v[j];
+    add_vec_f32<NV>(o, bias + col0);
+    for (int b = 0; b < beams; ++b)
+      store_bf16_vec<NV>(kv.cache + kv.offset(col0 >> 11, (col0 >> 10) & 1, row * beams + b, (col0 & 1023) >> 6, 0) + (col0 & 63), o);
   }
 };
 
 // lm_head epilogue for greedy decoding (language_model.py:366 + :632): the [rows, 50257] logits are never
-// materialised; every CTA emits the (max, first arg-max) of its 128 x BN tile per row.
+// materialised; every epilogue thread emits the (max, first arg-max) of the columns it saw for its row.
 struct EpiArgmaxPartial {
   struct State {
     float best;
     int idx;
   };
   static constexpr bool kDirect = true;  // reduction along N: one row per thread, no transpose
-  float* part_val;  // [M, n_tiles]
-  int* part_idx;    // [M, n_tiles]
-  int n_tiles;
+  float* part_val;  // [M, n_parts]
+  int* part_idx;    // [M, n_parts]
+  int n_parts;
 
-  __device__ __forceinline__ void init(State& s) const {
+  __device__ __forceinline__ void init(State& s, int) const {
     s.best = -INFINITY;
     s.idx = 0x7fffffff;
   }
@@ -178,9 +212,9 @@ struct EpiArgmaxPartial {
       }
     }
   }
-  __device__ __forceinline__ void finish(State& s, int row, int n_blk) const {
-    part_val[static_cast<size_t>(row) * n_tiles + n_blk] = s.best;
-    part_idx[static_cast<size_t>(row) * n_tiles + n_blk] = s.idx;
+  __device__ __forceinline__ void finish(State& s, int row, int part) const {
+    part_val[static_cast<size_t>(row) * n_parts + part] = s.best;
+    part_idx[static_cast<size_t>(row) * n_parts + part] = s.idx;
   }
 };
 

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const TA* __restrict__ A
     const int row = m0 + ty * 4 + i;
     if (row < M && col0 < N) {
       typename Epi::State st;
-      epi.init(st);
+      epi.init(st, 0);
       epi.template apply<4>(st, row, col0, acc[i], N);
     }
   }

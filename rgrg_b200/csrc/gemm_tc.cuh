@@ -19,7 +19,8 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                        // two warps per TMEM lane quarter, alternating 16-column chunks
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 struct GemmShape {
   int M, N;
@@ -31,6 +32,8 @@ struct GemmShape {
   int kc_blocks;         // Cin / 64
   int H, W;              // activation height / width
   int tiles_w, tiles_h;  // output tiles per image: (W/16) x (H/8); one tile = 8 rows x 16 cols = 128 pixels
+  long long* trace;      // optional [grid, 8] clock64 timeline of each CTA (bring-up / tuning only)
+  int k_splits;          // split-K factor (0/1 = off): tile index -> (split, m, n); each split covers k_iters / k_splits blocks
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -130,6 +133,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* r) 
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled operand tile in shared memory (rows of 64 bf16 = 128 B; 8-row groups 1024 B apart).
@@ -154,8 +166,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-constexpr int EPI_WARPS = 4;
-constexpr int STG_LD = 36;  // staging row stride in floats (32 + 4): 16-byte aligned rows, conflict-free quarter-warps
+constexpr int STG_FLOATS = 32 * 16;  // per-warp transpose buffer: 32 rows x 16 columns fp32, XOR-swizzled 16-byte chunks
 
 template <int BN, int STAGES>
 struct SmemLayout {
@@ -163,7 +174,7 @@ struct SmemLayout {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STG_BYTES = EPI_WARPS * 32 * STG_LD * 4;
+  static constexpr int STG_BYTES = EPI_WARPS * STG_FLOATS * 4;
   static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
   static_assert(TOTAL <= 232448, "shared memory budget exceeded");
@@ -176,10 +187,16 @@ constexpr int tmem_cols() {  // two accumulator stages, power of two >= 32
 }
 
 struct TileCoord {
-  int m_blk, n_blk, img, h0, w0;
+  int m_blk, n_blk, img, h0, w0, split;
 };
 __device__ __forceinline__ TileCoord tile_coord(const GemmShape& s, int tile) {
   TileCoord c;
+  c.split = 0;
+  if (s.k_splits > 1) {
+    const int per = s.m_tiles * s.n_tiles;
+    c.split = tile / per;
+    tile -= c.split * per;
+  }
   if (s.m_fastest) {
     c.m_blk = tile % s.m_tiles;
     c.n_blk = tile / s.m_tiles;
@@ -203,8 +220,10 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmShape& s, int tile) {
 // the epilogue of tile i overlaps the main loop of tile i+1.
 //   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + MMA issuer (one lane issues tcgen05.mma; tcgen05.commit frees ring slots)
-//   warps 2..5  : epilogue: tcgen05.ld 32x32b (lane = row) -> smem transpose -> 8 consecutive columns per lane
-//                 -> fused epilogue functor with 16-byte coalesced global accesses
+//   warps 2..9  : epilogue, two warps per TMEM lane quarter alternating 16-column chunks: tcgen05.ld 32x32b.x16
+//                 (lane = row) -> swizzled smem transpose -> 8 consecutive columns per lane -> fused epilogue functor
+//                 with 16-byte coalesced global accesses.  (One warp per scheduler cannot hide its own latency: the
+//                 4-warp version of this epilogue needed 14 us for a 128x192 tile, 3x the tile's MMA time.)
 // ---------------------------------------------------------------------------------------------------------------
 template <int BN, int STAGES, class Epi>
 __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -221,7 +240,10 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = s.m_tiles * s.n_tiles;
+  const int num_tiles = s.m_tiles * s.n_tiles * (s.k_splits > 1 ? s.k_splits : 1);
+  const int k_per_tile = s.k_splits > 1 ? s.k_iters / s.k_splits : s.k_iters;
+  long long* trace = s.trace ? s.trace + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
+  if (trace && threadIdx.x == 0) trace[0] = clock64();
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -246,17 +268,39 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (trace && threadIdx.x == 0) trace[1] = clock64();
+  // PDL: everything above overlapped the predecessor's tail; let our own successor get scheduled early as well
+  griddep_launch_dependents();
+  const bool is_producer = (warp == 0 && lane == 0);
+  if (!is_producer) griddep_wait();
 
   if (warp == 0) {
     if (lane == 0) {
+      // Weights (operand B) never depend on the predecessor kernel: start streaming the first ring of W tiles before
+      // waiting for it; the activation tiles (operand A) follow after griddep_wait().
+      int prefetched = 0;
+      if (blockIdx.x < num_tiles) {
+        const TileCoord t0 = tile_coord(s, blockIdx.x);
+        const int kb0 = t0.split * k_per_tile;
+        prefetched = k_per_tile < STAGES ? k_per_tile : STAGES;
+        for (int i = 0; i < prefetched; ++i) {
+          mbar_expect_tx(&full_bar[i], L::STAGE_BYTES);
+          tma_load_2d(smem + i * L::STAGE_BYTES + L::A_BYTES, &tmB, &full_bar[i], (kb0 + i) * BK, t0.n_blk * BN);
+        }
+      }
+      griddep_wait();
       int kbg = 0;  // k-block counter across tiles: ring slot = kbg % STAGES
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord tc_ = tile_coord(s, tile);
-        for (int kb = 0; kb < s.k_iters; ++kb, ++kbg) {
+        const int kb_end = (tc_.split + 1) * k_per_tile;
+        for (int kb = tc_.split * k_per_tile; kb < kb_end; ++kb, ++kbg) {
           const int st = kbg % STAGES;
           const uint32_t ph = (kbg / STAGES) & 1;
-          mbar_wait(&empty_bar[st], ph ^ 1);
-          mbar_expect_tx(&full_bar[st], L::STAGE_BYTES);
+          const bool early_b = kbg < prefetched;  // this slot's barrier is armed and its W tile already in flight
+          if (!early_b) {
+            mbar_wait(&empty_bar[st], ph ^ 1);
+            mbar_expect_tx(&full_bar[st], L::STAGE_BYTES);
+          }
           uint8_t* a_dst = smem + st * L::STAGE_BYTES;
           uint8_t* b_dst = a_dst + L::A_BYTES;
           if (s.conv) {
@@ -267,7 +311,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
           } else {
             tma_load_2d(a_dst, &tmA, &full_bar[st], kb * BK, tc_.m_blk * BM);
           }
-          tma_load_2d(b_dst, &tmB, &full_bar[st], kb * BK, tc_.n_blk * BN);
+          if (!early_b) tma_load_2d(b_dst, &tmB, &full_bar[st], kb * BK, tc_.n_blk * BN);
         }
       }
     }
@@ -281,11 +325,12 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < s.k_iters; ++kb, ++kbg) {
+        for (int kb = 0; kb < k_per_tile; ++kb, ++kbg) {
           const int st = kbg % STAGES;
           const uint32_t ph = (kbg / STAGES) & 1;
           mbar_wait(&full_bar[st], ph);
           tc_fence_after();
+          if (trace && kbg == 0) trace[2] = clock64();
           const uint32_t a_addr = smem_u32(smem + st * L::STAGE_BYTES);
           const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
           const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + L::A_BYTES);
@@ -297,11 +342,13 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
           umma_commit(&empty_bar[st]);  // ring slot reusable once these MMAs have read it
         }
         umma_commit(&tmem_full_bar[acc]);  // accumulator stage complete
+        if (trace) trace[3] = clock64();
       }
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
-    float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET) + (warp - 2) * 32 * STG_LD;
+    const int q = warp & 3;            // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
+    const int half = (warp - 2) >> 2;  // which of the two warps of that quarter: takes 16-column chunks half, half+2, ...
+    float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET) + (warp - 2) * STG_FLOATS;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc_ = tile_coord(s, tile);
@@ -309,80 +356,83 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
       const uint32_t acc_ph = (it >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
+      if (trace && warp == 2 && lane == 0 && it == 0) trace[4] = clock64();
       const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      typename Epi::State st;
+      epi.init(st, tc_.split);
       if constexpr (Epi::kDirect) {
         // one row per thread, straight from registers (reductions along N: the arg-max epilogue)
         const int r = q * 32 + lane;
-        int row;
-        bool row_ok;
-        if (s.conv) {
-          row = (tc_.img * s.H + tc_.h0 + (r >> 4)) * s.W + tc_.w0 + (r & 15);
-          row_ok = true;
-        } else {
-          row = tc_.m_blk * BM + r;
-          row_ok = row < s.M;
-        }
-        typename Epi::State st;
-        epi.init(st);
+        const int row = tc_.m_blk * BM + r;
+        const bool row_ok = row < s.M;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_addr + c, v);
+        for (int c = half * 16; c < BN; c += 32) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_addr + c, v);
           tmem_ld_wait();
           const int col0 = tc_.n_blk * BN + c;
-          if (row_ok && col0 < s.N) epi.template apply<32>(st, row, col0, reinterpret_cast<const float*>(v), s.N);
+          if (row_ok && col0 < s.N) epi.template apply<16>(st, row, col0, reinterpret_cast<const float*>(v), s.N);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-        if (row_ok) epi.finish(st, row, tc_.n_blk);
+        if (row_ok) epi.finish(st, row, tc_.n_blk * 2 + half);
       } else {
-        typename Epi::State st;
-        epi.init(st);
+        // rows of the two transposed passes this lane stores: lane>>1 and 16 + lane>>1 of the warp's 32
+        int rows[2];
+        bool rows_ok[2];
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          const int r = q * 32 + pass * 16 + (lane >> 1);
+          if (s.conv) {
+            rows[pass] = (tc_.img * s.H + tc_.h0 + (r >> 4)) * s.W + tc_.w0 + (r & 15);
+            rows_ok[pass] = true;
+          } else {
+            rows[pass] = tc_.m_blk * BM + r;
+            rows_ok[pass] = rows[pass] < s.M;
+          }
+        }
+        const int sw_w = (lane >> 1) & 3;  // XOR swizzle of this lane's own row when writing (row = lane)
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_addr + c, v);
+        for (int c = half * 16; c < BN; c += 32) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_addr + c, v);
           tmem_ld_wait();
-          if (c + 32 >= BN) {  // last read of this accumulator stage: hand it back to the MMA warp
+          if (c + 32 >= BN) {  // this warp's last read of the accumulator stage: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
           }
-          // transpose through shared memory: thread = row  ->  lane = 8 consecutive columns of 8 rows per pass
-          float4* dst = reinterpret_cast<float4*>(stg + lane * STG_LD);
+          // transpose through shared memory: thread = row  ->  lane = 8 consecutive columns of 2 rows.
+          // 16-byte chunk j of row r lives at slot r*4 + (j ^ ((r>>1)&3)): conflict-free for both phases.
+          float4* wr = reinterpret_cast<float4*>(stg) + lane * 4;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                                 __uint_as_float(v[4 * j + 3]));
+          for (int j = 0; j < 4; ++j)
+            wr[j ^ sw_w] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                       __uint_as_float(v[4 * j + 3]));
           __syncwarp();
-          const int col0 = tc_.n_blk * BN + c + (lane & 3) * 8;
+          const int col0 = tc_.n_blk * BN + c + (lane & 1) * 8;
+          const bool col_ok = col0 < s.N;
 #pragma unroll
-          for (int pass = 0; pass < 4; ++pass) {
-            const int rl = pass * 8 + (lane >> 2);  // row within this warp's 32
-            const int r = q * 32 + rl;
-            int row;
-            bool row_ok;
-            if (s.conv) {
-              row = (tc_.img * s.H + tc_.h0 + (r >> 4)) * s.W + tc_.w0 + (r & 15);
-              row_ok = true;
-            } else {
-              row = tc_.m_blk * BM + r;
-              row_ok = row < s.M;
-            }
-            const float4* src = reinterpret_cast<const float4*>(stg + rl * STG_LD + (lane & 3) * 8);
-            const float4 x0 = src[0], x1 = src[1];
+          for (int pass = 0; pass < 2; ++pass) {
+            const int rl = pass * 16 + (lane >> 1);
+            const int sw_r = (rl >> 1) & 3;
+            const float4* rd = reinterpret_cast<const float4*>(stg) + rl * 4;
+            const int j0 = (lane & 1) * 2;
+            const float4 x0 = rd[j0 ^ sw_r], x1 = rd[(j0 + 1) ^ sw_r];
             const float vals[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-            if (row_ok && col0 < s.N) epi.template apply<8>(st, row, col0, vals, s.N);
+            if (rows_ok[pass] && col_ok) epi.template apply<8>(st, rows[pass], col0, vals, s.N);
           }
           __syncwarp();
         }
       }
     }
   }
+  if (trace && warp == 2 && lane == 0) trace[5] = clock64();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols<BN>());
+  if (trace && threadIdx.x == 0) trace[6] = clock64();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -443,7 +493,7 @@ inline int num_sms() {
 
 template <int BN, int STAGES, class Epi>
 inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const Epi& epi,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, bool pdl = false) {
   using L = SmemLayout<BN, STAGES>;
   auto kern = gemm_tc_kernel<BN, STAGES, Epi>;
   static bool configured = false;  // one static per template instantiation
@@ -451,10 +501,9 @@ inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmSha
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  const int tiles = s.m_tiles * s.n_tiles;
+  const int tiles = s.m_tiles * s.n_tiles * (s.k_splits > 1 ? s.k_splits : 1);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, s, epi);
-  KERNEL_CHECK();
+  launch_kernel(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, stream, pdl, tmA, tmB, s, epi);
 }
 
 }  // namespace tc

@@ -193,6 +193,13 @@ class Engine:
                                              int(M), int(N), int(K), int(act), int(impl), _ptr(out), _stream(self.device)))
         return out
 
+    def gemm_bench(self, M, N, K, bn, iters=50, interleave=False, trace_ctas=0):
+        ms = C.c_float(0)
+        trace = np.zeros((max(trace_ctas, 1), 8), dtype=np.int64)
+        self._check(self._lib.rgrg_gemm_bench(self._h, M, N, K, bn, iters, int(interleave), C.byref(ms),
+                                              _ptr(trace) if trace_ctas else None, trace_ctas))
+        return ms.value, trace
+
     def conv3x3(self, x_nhwc_bf16, w_bf16, bias=None, relu=False, implicit=True):
         B, H, W, Cin = x_nhwc_bf16.shape
         Cout = w_bf16.shape[0]

@@ -94,6 +94,19 @@ def main():
             ms /= n
             print("perf impl=%d M=%d N=%d K=%d: %.4f ms  %.1f TFLOP/s (CUDA events around the kernel, fp32 store epilogue)" %
                   (impl, M, N, K, ms, 2.0 * M * N * K / ms / 1e9), flush=True)
+    elif step == "timeline":
+        import numpy as np
+        for (M, N, K, bn) in [(928, 3072, 1024, 192), (928, 4096, 1024, 256), (928, 4096, 1024, 128), (928, 1024, 4096, 64),
+                              (928, 1024, 1024, 64), (928, 50257, 1024, 256), (8192, 8192, 1024, 256)]:
+            for inter in (False, True):
+                tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+                ctas = min(tiles, 148)
+                ms, tr = e.gemm_bench(M, N, K, bn, 50, inter, ctas)
+                tr = tr.astype(np.float64)
+                d = lambda i, j: (tr[:, i] - tr[:, j]).mean() / 1.965e3  # us at 1965 MHz
+                print("M=%d N=%d K=%d bn=%d ln_interleaved=%d: %.2f us/iter | CTA timeline us (mean): setup %.2f, first-data %.2f, "
+                      "mma-issue-done %.2f, epi-start %.2f, epi-done %.2f, exit %.2f (tiles/cta %.1f)" %
+                      (M, N, K, bn, inter, ms * 1e3, d(1, 0), d(2, 0), d(3, 0), d(4, 0), d(5, 0), d(6, 0), tiles / ctas), flush=True)
     print("step %s done" % step, flush=True)
 
 
