@@ -90,8 +90,11 @@ __device__ __forceinline__ float warp_max(float v) {
 // transformers activations.py NewGELUActivation: 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
 __device__ __forceinline__ float gelu_new(float x) {
   const float k = 0.7978845608028654f;
-  float inner = k * (x + 0.044715f * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(inner));
+  const float inner = k * (x + 0.044715f * x * x * x);
+  float t;
+  // MUFU.TANH: max abs error ~5e-4, below the bf16 rounding (2^-9 relative) applied to the result right after
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
+  return 0.5f * x * (1.0f + t);
 }
 
 }  // namespace rgrg

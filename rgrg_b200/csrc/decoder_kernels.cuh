@@ -117,19 +117,19 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
   const int sent_row0 = anc ? (row / nb) * nb : 0;
   const unsigned char* arow = anc ? anc + static_cast<size_t>(row) * anc_ld : nullptr;
 
-  // online softmax: each of the 4 key subgroups keeps its own running (max, denominator, accumulator); K and V of a
-  // key are fetched together so both 16-byte loads are in flight before the dependent math
+  // Online softmax; each of the 4 key subgroups keeps its own running (max, denominator, accumulator).
+  // Keys are processed 16 at a time (4 per subgroup): all eight 16-byte loads of a chunk are issued before any of the
+  // dependent math, and the next chunk's loads are issued before the current chunk is reduced (register double buffer),
+  // so a warp keeps 8-16 independent 512-byte requests in flight.
   float m = -INFINITY, den = 0.0f;
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
-  const int iters = (L + 3) >> 2;
-#pragma unroll 4
-  for (int i = 0; i < iters; ++i) {
-    const int key = i * 4 + sub;
-    const bool ok = key < L;
-    uint4 kraw = make_uint4(0, 0, 0, 0), vraw = make_uint4(0, 0, 0, 0);
-    if (ok) {
+  auto load_chunk = [&](int c0, uint4* kr, uint4* vr) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int key = c0 + i * 4 + sub;
+      key = key < L ? key : L - 1;  // clamp: in-bounds address, masked out below
       const bf16* kp = Kp;
       const bf16* vp = Vp;
       if (anc) {
@@ -137,27 +137,51 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
         kp = kv.cache + kv.offset(layer, 0, prow, head, 0);
         vp = kv.cache + kv.offset(layer, 1, prow, head, 0);
       }
-      kraw = *reinterpret_cast<const uint4*>(kp + static_cast<size_t>(key) * HD + dseg * 8);
-      vraw = *reinterpret_cast<const uint4*>(vp + static_cast<size_t>(key) * HD + dseg * 8);
+      kr[i] = *reinterpret_cast<const uint4*>(kp + static_cast<size_t>(key) * HD + dseg * 8);
+      vr[i] = *reinterpret_cast<const uint4*>(vp + static_cast<size_t>(key) * HD + dseg * 8);
     }
-    float kf[8], vf[8];
-    unpack8(kraw, kf);
-    unpack8(vraw, vf);
-    float part = 0.0f;
+  };
+  uint4 kcur[4], vcur[4], knext[4], vnext[4];
+  load_chunk(0, kcur, vcur);
+  for (int c0 = 0; c0 < L; c0 += 16) {
+    const bool more = c0 + 16 < L;
+    if (more) load_chunk(c0 + 16, knext, vnext);
+    float sc[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) part = fmaf(qv[e], kf[e], part);
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    part += __shfl_xor_sync(0xffffffffu, part, 4);
-    if (ok) {
-      const float sc = part * 0.125f;  // / sqrt(64)   (language_model.py:88)
-      const float m_new = fmaxf(m, sc);
+    for (int i = 0; i < 4; ++i) {
+      float kf[8];
+      unpack8(kcur[i], kf);
+      float part = 0.0f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) part = fmaf(qv[e], kf[e], part);
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      sc[i] = (c0 + i * 4 + sub < L) ? part * 0.125f : -INFINITY;  // / sqrt(64)   (language_model.py:88)
+    }
+    const float m_new = fmaxf(fmaxf(m, fmaxf(sc[0], sc[1])), fmaxf(sc[2], sc[3]));
+    if (m_new > -INFINITY) {
       const float corr = __expf(m - m_new);
-      const float p = __expf(sc - m_new);
-      den = fmaf(den, corr, p);
+      den *= corr;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = fmaf(acc[e], corr, p * vf[e]);
+      for (int e = 0; e < 8; ++e) acc[e] *= corr;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float p = __expf(sc[i] - m_new);  // exp(-inf) = 0 for masked keys
+        den += p;
+        float vf[8];
+        unpack8(vcur[i], vf);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vf[e], acc[e]);
+      }
       m = m_new;
+    }
+    if (more) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        kcur[i] = knext[i];
+        vcur[i] = vnext[i];
+      }
     }
   }
   // merge the 4 key subgroups (lanes differing in bits 3 and 4)

@@ -170,6 +170,7 @@ struct rgrg_engine {
   int opt_cuda_graph = 1;
   int opt_gemm_impl = 0;
   int opt_pdl = 1;
+  int opt_ablate = 0;  // tuning only: bit mask of decode-step kernels to skip (results become meaningless, timing attributes cost)
   bool pdl_now = false;  // set while the decode step is being issued: its kernels carry the PDL launch attribute
   std::unordered_map<std::string, HostRef> host;
   std::vector<void*> weight_allocs;
@@ -877,6 +878,10 @@ struct rgrg_engine {
     const float* pending_bias = nullptr;
     auto ln = [&](const float* g, const float* b) {
       ProfScope ps(this, "layernorm", st);
+      if (opt_ablate & 2) {
+        pending_bias = nullptr;
+        return;
+      }
       if (pending_bias)
         launch_kernel(dec::layernorm_kernel<SPLITS>, dim3(ln_grid), dim3(256), 0, st, pdl_now, h.as<float>(), g, b, x.as<bf16>(), rows,
                       parts, pstride, pending_bias);
@@ -890,18 +895,19 @@ struct rgrg_engine {
       const LayerW& L = layers[l];
       ln(L.ln1_g, L.ln1_b);
       EpiQkvAppend eq{q.as<bf16>(), L.attn.bias, kv_geom(), l, sp};
-      gemm("c_attn", x.as<bf16>(), rows, L.attn, eq, st, true);
-      {
+      if (!(opt_ablate & 4)) gemm("c_attn", x.as<bf16>(), rows, L.attn, eq, st, true);
+      if (!(opt_ablate & 1)) {
         ProfScope ps(this, "attention", st);
         launch_kernel(dec::attention_kernel, dim3(ceil_div(rows * 16, 4)), dim3(128), 0, st, pdl_now, q.as<bf16>(), kv_geom(), l, sp,
                       attn_o.as<bf16>(), rows, beam_anc, beam_slots, beam_nb);
         ++launches;
       }
-      gemm_splitk("attn_c_proj", attn_o.as<bf16>(), rows, L.proj, parts, SPLITS, st);
+      if (!(opt_ablate & 8)) gemm_splitk("attn_c_proj", attn_o.as<bf16>(), rows, L.proj, parts, SPLITS, st);
       pending_bias = L.proj.bias;
       ln(L.ln2_g, L.ln2_b);
-      gemm("mlp_c_fc", x.as<bf16>(), rows, L.fc, epi<true, ACT_GELU_NEW, RES_NONE, true>(mlp_mid.p, L.fc.bias, 4 * DM), st, true);
-      gemm_splitk("mlp_c_proj", mlp_mid.as<bf16>(), rows, L.mproj, parts, SPLITS, st);
+      if (!(opt_ablate & 16))
+        gemm("mlp_c_fc", x.as<bf16>(), rows, L.fc, epi<true, ACT_GELU_NEW, RES_NONE, true>(mlp_mid.p, L.fc.bias, 4 * DM), st, true);
+      if (!(opt_ablate & 32)) gemm_splitk("mlp_c_proj", mlp_mid.as<bf16>(), rows, L.mproj, parts, SPLITS, st);
       pending_bias = L.mproj.bias;
     }
     ln(lnf_g, lnf_b);
@@ -1272,6 +1278,12 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "cuda_graph") e->opt_cuda_graph = value;
   else if (k == "gemm_impl") e->opt_gemm_impl = value;
   else if (k == "pdl") e->opt_pdl = value;
+  else if (k == "ablate") {
+    e->opt_ablate = value;
+    for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.second);
+    e->step_graphs.clear();
+    e->step_graph_nodes.clear();
+  }
   else {
     e->err = "unknown option: " + k;
     return 1;

@@ -1,0 +1,37 @@
+"""Attribute decode-step time to kernel groups by ablation under CUDA-graph replay (results are meaningless when a
+kernel is skipped; only the timing is used).  python tools/ablate.py"""
+import os, sys, time
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from rgrg_b200 import ReportGenerationModel, synth
+
+sd = synth.make_state_dict(0)
+m = ReportGenerationModel(True); m.load_state_dict(sd); m.to(torch.device("cuda", 0)); m.eval()
+eng = m._engine()
+feats = torch.randn(928, 1024, generator=torch.Generator().manual_seed(1)).cuda()
+T = 64
+
+def run(mask, pdl=1, graph=1):
+    eng.set_option("ablate", mask); eng.set_option("pdl", pdl); eng.set_option("cuda_graph", graph)
+    for _ in range(2):
+        eng.lm_generate(feats, T)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n = 3
+    for _ in range(n):
+        eng.lm_generate(feats, T)
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / n / (T - 1) * 1e3  # ms per decode step
+
+base = run(0)
+print("full step                : %.3f ms" % base, flush=True)
+print("full step, PDL off       : %.3f ms" % run(0, pdl=0), flush=True)
+print("full step, eager no graph: %.3f ms" % run(0, graph=0), flush=True)
+configs = [("attention", 1), ("layernorm", 2), ("c_attn", 4), ("attn_c_proj", 8), ("mlp_c_fc", 16), ("mlp_c_proj", 32),
+           ("all GEMMs of the layers", 4 | 8 | 16 | 32), ("everything in the layers", 63)]
+if len(sys.argv) > 1:
+    configs = [c for c in configs if c[0] in sys.argv[1:]]
+for name, mask in configs:
+    t = run(mask)
+    print("without %-24s: %.3f ms  (saves %.3f ms = %.1f us per layer)" % (name, t, base - t, (base - t) / 24 * 1e3), flush=True)
