@@ -24,33 +24,34 @@ __device__ __forceinline__ float float_from_key_dec(unsigned k) {
 
 // K15  h[r] = wte[token] + wte[position]   — positions are embedded through wte, not wpe (language_model.py:307)
 // token of row r at step t = ids[r, t]; position = t.
+// one warp embeds one row (32 floats per lane)
+__device__ __forceinline__ void embed_row_dev(const float* __restrict__ wte, int tok, int pos, float* __restrict__ hrow, int lane) {
+  const float4* a = reinterpret_cast<const float4*>(wte + static_cast<size_t>(tok) * D);
+  const float4* p = reinterpret_cast<const float4*>(wte + static_cast<size_t>(pos) * D);
+  float4* o = reinterpret_cast<float4*>(hrow);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 x = a[i * 32 + lane], y = p[i * 32 + lane];
+    o[i * 32 + lane] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+  }
+}
 __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ wte, const int* __restrict__ ids, int ids_ld,
-                                                    const int* __restrict__ step_ptr, float* __restrict__ h) {
+                                                    const int* __restrict__ step_ptr, float* __restrict__ h, int rows) {
   griddep_wait();
   griddep_launch_dependents();
-  const int r = blockIdx.x;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
   const int t = *step_ptr;
-  const int tok = ids[static_cast<size_t>(r) * ids_ld + t];
-  const float4* a = reinterpret_cast<const float4*>(wte + static_cast<size_t>(tok) * D);
-  const float4* p = reinterpret_cast<const float4*>(wte + static_cast<size_t>(t) * D);
-  float4* o = reinterpret_cast<float4*>(h + static_cast<size_t>(r) * D);
-  const float4 x = a[threadIdx.x], y = p[threadIdx.x];
-  o[threadIdx.x] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+  embed_row_dev(wte, ids[static_cast<size_t>(r) * ids_ld + t], t, h + static_cast<size_t>(r) * D, threadIdx.x & 31);
 }
 
 // K16  LayerNorm(eps 1e-5) over 1024 features: fp32 residual stream -> bf16 GEMM operand.  One warp per row.
 // Fused with the residual update of the GEMM that precedes it (language_model.py:350, :357): when `parts` is given,
 // h <- h + bias + sum of the GEMM's split-K partial sums (written by its epilogue), stored back, then normalised.
 template <int NPARTS>
-__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ h, const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, bf16* __restrict__ out, int rows,
-                                                        const float* __restrict__ parts, size_t part_stride,
-                                                        const float* __restrict__ res_bias) {
-  griddep_wait();
-  griddep_launch_dependents();
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+__device__ __forceinline__ void ln_row_dev(float* __restrict__ h, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                           bf16* __restrict__ out, int row, int lane, const float* __restrict__ parts,
+                                           size_t part_stride, const float* __restrict__ res_bias) {
   float4* src = reinterpret_cast<float4*>(h + static_cast<size_t>(row) * D);
   float v[32];
   float sum = 0.0f;
@@ -62,7 +63,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ h, c
       x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
 #pragma unroll
       for (int p = 0; p < NPARTS; ++p) {
-        const float4 t = *reinterpret_cast<const float4*>(parts + p * part_stride + static_cast<size_t>(row) * D + (i * 32 + lane) * 4);
+        // partial sums come from other CTAs' epilogues: read through L2 (__ldcg), never from a possibly stale L1 line
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(parts + p * part_stride + static_cast<size_t>(row) * D + (i * 32 + lane) * 4));
         x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
       }
       src[i * 32 + lane] = x;
@@ -91,6 +93,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ h, c
     *reinterpret_cast<uint2*>(out + static_cast<size_t>(row) * D + c) = pk;
   }
 }
+template <int NPARTS>
+__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ h, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, bf16* __restrict__ out, int rows,
+                                                        const float* __restrict__ parts, size_t part_stride,
+                                                        const float* __restrict__ res_bias) {
+  griddep_wait();
+  griddep_launch_dependents();
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  ln_row_dev<NPARTS>(h, gamma, beta, out, row, threadIdx.x & 31, parts, part_stride, res_bias);
+}
 
 // K18  single-query attention over the in-place KV cache (language_model.py:84-114 for a 1-token query):
 // scores = q.K^T / 8 over slots [0, t+2) (slot 0 = image key), softmax in fp32, out = P.V.  The causal / padding
@@ -98,20 +111,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ h, c
 // lane l holds dims (l%8)*8..+8 of key 4*i + l/8.
 // Beam search: `anc` (optional) maps (row, slot) to the beam of the same sentence whose physical cache row holds that
 // slot, so the reference's per-step index_select of the whole cache (language_model.py:492-496) becomes a table lookup.
-__global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__ q, KvGeom kv, int layer,
-                                                        const int* __restrict__ step_ptr, bf16* __restrict__ out, int rows,
-                                                        const unsigned char* __restrict__ anc, int anc_ld, int nb) {
-  griddep_wait();
-  griddep_launch_dependents();
-  const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (gw >= rows * HEADS) return;
-  const int row = gw / HEADS, head = gw % HEADS;
-  const int L = *step_ptr + 2;
+__device__ __forceinline__ void attention_dev(const bf16* __restrict__ q, const KvGeom& kv, int layer, int L, bf16* __restrict__ out,
+                                              int row, int head, int lane, const unsigned char* __restrict__ anc, int anc_ld, int nb) {
   const int sub = lane >> 3, dseg = lane & 7;
 
   float qv[8];
-  unpack8(*reinterpret_cast<const uint4*>(q + static_cast<size_t>(row) * D + head * HD + dseg * 8), qv);
+  unpack8(__ldcg(reinterpret_cast<const uint4*>(q + static_cast<size_t>(row) * D + head * HD + dseg * 8)), qv);
   const bf16* Kp = kv.cache + kv.offset(layer, 0, row, head, 0);
   const bf16* Vp = kv.cache + kv.offset(layer, 1, row, head, 0);
   const int sent_row0 = anc ? (row / nb) * nb : 0;
@@ -137,8 +142,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
         kp = kv.cache + kv.offset(layer, 0, prow, head, 0);
         vp = kv.cache + kv.offset(layer, 1, prow, head, 0);
       }
-      kr[i] = *reinterpret_cast<const uint4*>(kp + static_cast<size_t>(key) * HD + dseg * 8);
-      vr[i] = *reinterpret_cast<const uint4*>(vp + static_cast<size_t>(key) * HD + dseg * 8);
+      kr[i] = __ldcg(reinterpret_cast<const uint4*>(kp + static_cast<size_t>(key) * HD + dseg * 8));  // streamed once: skip L1
+      vr[i] = __ldcg(reinterpret_cast<const uint4*>(vp + static_cast<size_t>(key) * HD + dseg * 8));
     }
   };
   uint4 kcur[4], vcur[4], knext[4], vnext[4];
@@ -205,6 +210,15 @@ __global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__
     *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * D + head * HD + dseg * 8) = pack8(acc);
   }
 }
+__global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__ q, KvGeom kv, int layer,
+                                                        const int* __restrict__ step_ptr, bf16* __restrict__ out, int rows,
+                                                        const unsigned char* __restrict__ anc, int anc_ld, int nb) {
+  griddep_wait();
+  griddep_launch_dependents();
+  const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (gw >= rows * HEADS) return;
+  attention_dev(q, kv, layer, *step_ptr + 2, out, gw / HEADS, gw % HEADS, threadIdx.x & 31, anc, anc_ld, nb);
+}
 
 // K22/K23  arg-max over the vocabulary + greedy bookkeeping (language_model.py:629-650).  One CTA.
 //   next = argmax(logits) (lowest index on ties); finished rows emit pad; ids[:, t+1] = next; a row finishes when it
@@ -221,52 +235,55 @@ struct GreedyState {
   int* argmax_out;   // optional [max_steps, rows] raw arg-max per step (tests)
 };
 
+// one warp: arg-max of one row + greedy bookkeeping
+__device__ __forceinline__ void greedy_row_dev(const float* __restrict__ part_val, const int* __restrict__ part_idx, int n_tiles,
+                                               const float* __restrict__ logits, const GreedyState& g, int rows, int r, int t,
+                                               int lane) {
+  float best = -INFINITY;
+  int idx = 0x7fffffff;
+  if (logits) {
+    const float* l = logits + static_cast<size_t>(r) * VOCAB;
+    for (int c = lane; c < VOCAB; c += 32) {
+      const float v = __ldcg(l + c);
+      if (v > best) { best = v; idx = c; }
+    }
+  } else {
+    for (int c = lane; c < n_tiles; c += 32) {
+      const float v = __ldcg(part_val + static_cast<size_t>(r) * n_tiles + c);
+      const int i = __ldcg(part_idx + static_cast<size_t>(r) * n_tiles + c);
+      if (v > best || (v == best && i < idx)) { best = v; idx = i; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+  }
+  if (lane == 0) {
+    if (g.argmax_out) g.argmax_out[static_cast<size_t>(t) * rows + r] = idx;
+    int nxt = idx;
+    int unf = g.unfinished[r];
+    const bool in_range = t + 1 < g.ids_ld;
+    if (g.forced) {
+      nxt = in_range ? g.forced[static_cast<size_t>(r) * g.ids_ld + t + 1] : EOS_ID;
+    } else {
+      if (!unf) nxt = EOS_ID;
+      if (nxt == EOS_ID) unf = 0;
+      g.unfinished[r] = unf;
+    }
+    if (in_range) g.ids[static_cast<size_t>(r) * g.ids_ld + t + 1] = nxt;
+    if (unf) atomicAdd(&g.unfinished_count[t], 1);
+  }
+}
 __global__ void __launch_bounds__(256) greedy_update_kernel(const float* __restrict__ part_val, const int* __restrict__ part_idx,
                                                             int n_tiles, const float* __restrict__ logits /*or null*/,
                                                             GreedyState g, int rows) {
   // one warp per row, 8 rows per CTA; the last CTA to finish publishes step + 1 (all CTAs read the step first)
   griddep_wait();
   const int t = *g.step_ptr;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * 8 + warp;
-  if (r < rows) {
-    float best = -INFINITY;
-    int idx = 0x7fffffff;
-    if (logits) {
-      const float* l = logits + static_cast<size_t>(r) * VOCAB;
-      for (int c = lane; c < VOCAB; c += 32) {
-        const float v = l[c];
-        if (v > best) { best = v; idx = c; }
-      }
-    } else {
-      for (int c = lane; c < n_tiles; c += 32) {
-        const float v = part_val[static_cast<size_t>(r) * n_tiles + c];
-        const int i = part_idx[static_cast<size_t>(r) * n_tiles + c];
-        if (v > best || (v == best && i < idx)) { best = v; idx = i; }
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-      if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
-    }
-    if (lane == 0) {
-      if (g.argmax_out) g.argmax_out[static_cast<size_t>(t) * rows + r] = idx;
-      int nxt = idx;
-      int unf = g.unfinished[r];
-      const bool in_range = t + 1 < g.ids_ld;
-      if (g.forced) {
-        nxt = in_range ? g.forced[static_cast<size_t>(r) * g.ids_ld + t + 1] : EOS_ID;
-      } else {
-        if (!unf) nxt = EOS_ID;
-        if (nxt == EOS_ID) unf = 0;
-        g.unfinished[r] = unf;
-      }
-      if (in_range) g.ids[static_cast<size_t>(r) * g.ids_ld + t + 1] = nxt;
-      if (unf) atomicAdd(&g.unfinished_count[t], 1);
-    }
-  }
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r < rows) greedy_row_dev(part_val, part_idx, n_tiles, logits, g, rows, r, t, threadIdx.x & 31);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();

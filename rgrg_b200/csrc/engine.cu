@@ -17,6 +17,7 @@
 #include "../../include/rgrg_b200.h"
 #include "common.cuh"
 #include "decoder_kernels.cuh"
+#include "decoder_megakernel.cuh"
 #include "detector_kernels.cuh"
 #include "epilogues.cuh"
 #include "gemm_simt.cuh"
@@ -170,6 +171,7 @@ struct rgrg_engine {
   int opt_cuda_graph = 1;
   int opt_gemm_impl = 0;
   int opt_pdl = 1;
+  int opt_megakernel = 0;  // greedy decode step as ONE persistent cooperative kernel (decoder_megakernel.cuh)
   int opt_ablate = 0;  // tuning only: bit mask of decode-step kernels to skip (results become meaningless, timing attributes cost)
   bool pdl_now = false;  // set while the decode step is being issued: its kernels carry the PDL launch attribute
   std::unordered_map<std::string, HostRef> host;
@@ -193,7 +195,8 @@ struct rgrg_engine {
   DevBuf lm_in;
   // ---- workspace (decoder)
   int ws_rows = 0, ws_slots = 0;
-  DevBuf splitk_parts;
+  DevBuf splitk_parts, mega_params, mega_sync;
+  int mega_rows = -1, mega_ld = -1;
   DevBuf kv_cache, h, x, q, attn_o, mlp_mid, a1, img, part_val, part_idx, ids, unfinished, unf_count, step, logits_tmp;
   int last_B = 0, last_S = 0, last_P = 0;
   // beam search: cache-slot ancestry of the current step (null in greedy mode)
@@ -214,7 +217,7 @@ struct rgrg_engine {
                      &prop_scores, &prop_count, &roi_off, &pooled, &f6, &f7, &pred_out, &detected, &top_idx,
                      &top_scores, &top_boxes, &mean2048, &trf, &s0, &s1, &sel_logits, &selected, &sel_rows, &num_sel,
                      &lm_in, &kv_cache, &h, &x, &q, &attn_o, &mlp_mid, &a1, &img, &part_val, &part_idx, &ids,
-                     &unfinished, &unf_count, &step, &logits_tmp, &splitk_parts, &b_ids2, &b_anc[0], &b_anc[1], &b_scores, &b_cand_score,
+                     &unfinished, &unf_count, &step, &logits_tmp, &splitk_parts, &mega_params, &mega_sync, &b_ids2, &b_anc[0], &b_anc[1], &b_scores, &b_cand_score,
                      &b_cand_token, &b_cand_beam, &b_hyp_score, &b_hyp_len, &b_hyp_tok, &b_hyp_count, &b_worst, &b_done, &b_not_done};
     for (DevBuf* b : all) b->release();
   }
@@ -845,6 +848,7 @@ struct rgrg_engine {
       step.ensure(16);
       ws_rows = r;
       ws_slots = s;
+      mega_rows = -1;
       for (auto& g : step_graphs) cudaGraphExecDestroy(g.second);  // buffers moved: captured pointers are stale
       step_graphs.clear();
       step_graph_nodes.clear();
@@ -866,7 +870,7 @@ struct rgrg_engine {
     const int* sp = step.as<int>();
     {
       ProfScope ps(this, "embed", st);
-      launch_kernel(dec::embed_kernel, dim3(rows), dim3(256), 0, st, false, wte_f32, ids_ptr, ids_ld, sp, h.as<float>());
+      launch_kernel(dec::embed_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, st, false, wte_f32, ids_ptr, ids_ld, sp, h.as<float>(), rows);
       ++launches;
     }
     pdl_now = opt_pdl != 0;
@@ -1108,6 +1112,85 @@ struct rgrg_engine {
     return beam_finalize(s, R, cur_len, cur, max_length, out_ids, st);
   }
 
+  // ---- the decode step as one persistent cooperative kernel
+  void mega_prepare(int rows, const dec::GreedyState& g) {
+    if (mega_rows == rows && mega_ld == g.ids_ld) return;
+    mega::Params* hp = new mega::Params();
+    memset(hp, 0, sizeof(mega::Params));
+    for (int l = 0; l < NLAYER; ++l) {
+      const LayerW& L = layers[l];
+      mega::Layer& d = hp->layer[l];
+      d.tm_attn = L.attn.tm[3];
+      d.tm_proj = L.proj.tm[3];
+      d.tm_fc = L.fc.tm[3];
+      d.tm_mproj = L.mproj.tm[3];
+      d.ln1_g = L.ln1_g; d.ln1_b = L.ln1_b; d.ln2_g = L.ln2_g; d.ln2_b = L.ln2_b;
+      d.b_attn = L.attn.bias; d.b_proj = L.proj.bias; d.b_fc = L.fc.bias; d.b_mproj = L.mproj.bias;
+    }
+    hp->tm_x = tc::make_tmap_2d(x.p, rows, DM, 128);
+    hp->tm_attn_o = tc::make_tmap_2d(attn_o.p, rows, DM, 128);
+    hp->tm_mid = tc::make_tmap_2d(mlp_mid.p, rows, 4 * DM, 128);
+    hp->tm_lm_head = lm_head.tm[3];
+    auto shape = [&](int N, int K, int splits) {
+      tc::GemmShape s{};
+      s.M = rows;
+      s.N = N;
+      s.k_iters = K / 64;
+      s.k_splits = splits;
+      s.m_tiles = ceil_div(rows, tc::BM);
+      s.n_tiles = ceil_div(N, mega::BN);
+      s.m_fastest = 1;
+      return s;
+    };
+    hp->s_attn = shape(3 * DM, DM, 0);
+    hp->s_proj = shape(DM, DM, mega::SPLITS);
+    hp->s_fc = shape(4 * DM, DM, 0);
+    hp->s_mproj = shape(DM, 4 * DM, mega::SPLITS);
+    hp->s_head = shape(VOCAB, DM, 0);
+    hp->lnf_g = lnf_g; hp->lnf_b = lnf_b; hp->wte = wte_f32;
+    hp->h = h.as<float>(); hp->x = x.as<bf16>(); hp->q = q.as<bf16>(); hp->attn_o = attn_o.as<bf16>(); hp->mid = mlp_mid.as<bf16>();
+    hp->parts = splitk_parts.as<float>();
+    hp->kv = kv_geom();
+    hp->g = g;
+    hp->part_val = part_val.as<float>();
+    hp->part_idx = part_idx.as<int>();
+    hp->n_parts = 2 * ceil_div(VOCAB, mega::BN);
+    hp->rows = rows;
+    mega_sync.ensure(64 + 256 * 8);
+    hp->sync_counter = mega_sync.as<unsigned>();
+    hp->trace = reinterpret_cast<long long*>(static_cast<char*>(mega_sync.p) + 64);
+    mega_params.ensure(sizeof(mega::Params));
+    cudaError_t err = cudaMemcpy(mega_params.p, hp, sizeof(mega::Params), cudaMemcpyHostToDevice);
+    delete hp;
+    CUDA_CHECK(err);
+    static bool configured = false;
+    if (!configured) {
+      CUDA_CHECK(cudaFuncSetAttribute(mega::decoder_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      tc::SmemLayout<mega::BN, mega::STAGES>::TOTAL));
+      configured = true;
+    }
+    mega_rows = rows;
+    mega_ld = g.ids_ld;
+  }
+  int decode_step_mega(int rows, cudaStream_t st) {
+    ProfScope ps(this, "decoder_step_megakernel", st);
+    CUDA_CHECK(cudaMemsetAsync(mega_sync.p, 0, 4, st));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(tc::num_sms());
+    cfg.blockDim = dim3(tc::NUM_THREADS);
+    cfg.dynamicSmemBytes = tc::SmemLayout<mega::BN, mega::STAGES>::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const mega::Params* dp = static_cast<const mega::Params*>(mega_params.p);
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, mega::decoder_step_kernel, dp));
+    launches += 1;
+    return 1;
+  }
+
   // greedy decode of `R` rows whose features sit in feats_bf16; host ids [R, max_length], returns reference width
   int run_greedy(const bf16* feats_bf16, int R, int max_length, int32_t* out_ids, cudaStream_t st) {
     ensure_decoder_ws(R, max_length);
@@ -1127,9 +1210,15 @@ struct rgrg_engine {
     cudaGraphExec_t exec = nullptr;
     int nodes = 0;
     const int graph_key = R * 4096 + max_length;
-    // step 0 always runs eagerly (it also makes sure every kernel is loaded and configured before a capture)
-    decode_step(R, g, nullptr, st);
-    if (opt_cuda_graph && !prof_on && steps > 1) {
+    const bool use_mega = opt_megakernel && opt_gemm_impl != 2 && !opt_ablate;
+    if (use_mega) {
+      mega_prepare(R, g);
+      decode_step_mega(R, st);
+    } else {
+      // step 0 always runs eagerly (it also makes sure every kernel is loaded and configured before a capture)
+      decode_step(R, g, nullptr, st);
+    }
+    if (!use_mega && opt_cuda_graph && !prof_on && steps > 1) {
       auto it = step_graphs.find(graph_key);
       if (it == step_graphs.end()) {
         cudaGraph_t graph;
@@ -1156,7 +1245,9 @@ struct rgrg_engine {
     int done_steps = 1;
     std::vector<int> counts(steps > 0 ? steps : 1);
     for (int t = 1; t < steps; ++t) {
-      if (exec) {
+      if (use_mega) {
+        decode_step_mega(R, st);
+      } else if (exec) {
         CUDA_CHECK(cudaGraphLaunch(exec, st));
         launches += nodes;
       } else {
@@ -1239,6 +1330,8 @@ int rgrg_create(int device, rgrg_engine_t** out) {
     e->device = device;
     const char* ic = getenv("RGRG_IMPLICIT_CONV");
     if (ic) e->opt_implicit_conv = atoi(ic);
+    const char* mk = getenv("RGRG_MEGAKERNEL");
+    if (mk) e->opt_megakernel = atoi(mk);
     *out = e;
     return 0;
   } catch (const std::exception& ex) {
@@ -1278,6 +1371,7 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "cuda_graph") e->opt_cuda_graph = value;
   else if (k == "gemm_impl") e->opt_gemm_impl = value;
   else if (k == "pdl") e->opt_pdl = value;
+  else if (k == "megakernel") e->opt_megakernel = value;
   else if (k == "ablate") {
     e->opt_ablate = value;
     for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.second);
@@ -1631,6 +1725,12 @@ int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst, size_t b
     else if (n == "selection_logits") b = &e->sel_logits;
     else if (n == "region_features_2048") b = &e->mean2048;
     else if (n == "fc7") b = &e->f7;
+    else if (n == "mega_trace") {
+      if (bytes > 256 * 8 || !e->mega_sync.p) throw std::runtime_error("no mega trace");
+      CUDA_CHECK(cudaDeviceSynchronize());
+      CUDA_CHECK(cudaMemcpy(host_dst, static_cast<char*>(e->mega_sync.p) + 64, bytes, cudaMemcpyDeviceToHost));
+      return 0;
+    }
     else throw std::runtime_error("unknown debug buffer: " + n);
     if (bytes > b->bytes) throw std::runtime_error("debug read larger than buffer: " + n);
     CUDA_CHECK(cudaDeviceSynchronize());

@@ -216,147 +216,160 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmShape& s, int tile) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The kernel: persistent (one CTA per SM walks tiles blockIdx.x, +gridDim.x, ...), two TMEM accumulator stages so
-// the epilogue of tile i overlaps the main loop of tile i+1.
+// The tile pipeline, written as device functions so that both the stand-alone GEMM kernel (below) and the decoder
+// mega-kernel (decoder_megakernel.cuh) run the same code.  A CTA is persistent: it walks tiles blockIdx.x, +gridDim.x,
+// ...; two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 //   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + MMA issuer (one lane issues tcgen05.mma; tcgen05.commit frees ring slots)
 //   warps 2..9  : epilogue, two warps per TMEM lane quarter alternating 16-column chunks: tcgen05.ld 32x32b.x16
 //                 (lane = row) -> swizzled smem transpose -> 8 consecutive columns per lane -> fused epilogue functor
 //                 with 16-byte coalesced global accesses.  (One warp per scheduler cannot hide its own latency: the
 //                 4-warp version of this epilogue needed 14 us for a 128x192 tile, 3x the tile's MMA time.)
+// Ring-slot and accumulator-stage counters (kbg, it) are carried by the caller, so consecutive GEMMs inside one
+// kernel keep the mbarrier phases consistent.
 // ---------------------------------------------------------------------------------------------------------------
-template <int BN, int STAGES, class Epi>
-__global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                               const __grid_constant__ CUtensorMap tmB,
-                                                               const GemmShape s, const Epi epi) {
+template <int BN, int STAGES>
+struct Pipe {
   using L = SmemLayout<BN, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint8_t* smem;
+  uint64_t *full_bar, *empty_bar, *tmem_full_bar, *tmem_empty_bar;
+  uint32_t tmem_base;
 
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int num_tiles = s.m_tiles * s.n_tiles * (s.k_splits > 1 ? s.k_splits : 1);
-  const int k_per_tile = s.k_splits > 1 ? s.k_iters / s.k_splits : s.k_iters;
-  long long* trace = s.trace ? s.trace + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
-  if (trace && threadIdx.x == 0) trace[0] = clock64();
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmB);
+  // barrier init + TMEM allocation; ends with a CTA-wide sync
+  __device__ __forceinline__ void setup(uint8_t* smem_raw) {
+    smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    empty_bar = full_bar + STAGES;
+    tmem_full_bar = empty_bar + STAGES;   // [2]
+    tmem_empty_bar = tmem_full_bar + 2;   // [2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
 #pragma unroll
-    for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-    }
+      for (int i = 0; i < STAGES; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], 1);
+      }
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], EPI_WARPS);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tmem_full_bar[i], 1);
+        mbar_init(&tmem_empty_bar[i], EPI_WARPS);
+      }
+      fence_barrier_init();
     }
-    fence_barrier_init();
+    if (warp == 1) {
+      tmem_alloc(tmem_ptr_smem, tmem_cols<BN>());
+      tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tmem_base = *tmem_ptr_smem;
   }
-  if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, tmem_cols<BN>());
-    tmem_relinquish();
+  __device__ __forceinline__ void teardown() {
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 1) tmem_dealloc(tmem_base, tmem_cols<BN>());
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  if (trace && threadIdx.x == 0) trace[1] = clock64();
-  // PDL: everything above overlapped the predecessor's tail; let our own successor get scheduled early as well
-  griddep_launch_dependents();
-  const bool is_producer = (warp == 0 && lane == 0);
-  if (!is_producer) griddep_wait();
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // Weights (operand B) never depend on the predecessor kernel: start streaming the first ring of W tiles before
-      // waiting for it; the activation tiles (operand A) follow after griddep_wait().
-      int prefetched = 0;
-      if (blockIdx.x < num_tiles) {
-        const TileCoord t0 = tile_coord(s, blockIdx.x);
-        const int kb0 = t0.split * k_per_tile;
-        prefetched = k_per_tile < STAGES ? k_per_tile : STAGES;
-        for (int i = 0; i < prefetched; ++i) {
-          mbar_expect_tx(&full_bar[i], L::STAGE_BYTES);
-          tma_load_2d(smem + i * L::STAGE_BYTES + L::A_BYTES, &tmB, &full_bar[i], (kb0 + i) * BK, t0.n_blk * BN);
+  static __device__ __forceinline__ int num_tiles(const GemmShape& s) { return s.m_tiles * s.n_tiles * (s.k_splits > 1 ? s.k_splits : 1); }
+  static __device__ __forceinline__ int k_per_tile(const GemmShape& s) { return s.k_splits > 1 ? s.k_iters / s.k_splits : s.k_iters; }
+
+  // producer, optional head start: arm the first ring slots of this CTA's first tile and start streaming their W
+  // (operand B) tiles, which never depend on a predecessor; returns how many k-blocks were started.
+  __device__ __forceinline__ int prefetch_w(const CUtensorMap* tmB, const GemmShape& s, int kbg) const {
+    if (static_cast<int>(blockIdx.x) >= num_tiles(s)) return 0;
+    const TileCoord t0 = tile_coord(s, blockIdx.x);
+    const int kpt = k_per_tile(s);
+    const int kb0 = t0.split * kpt;
+    const int n = kpt < STAGES ? kpt : STAGES;
+    for (int i = 0; i < n; ++i) {
+      const int st = (kbg + i) % STAGES;
+      const uint32_t ph = ((kbg + i) / STAGES) & 1;
+      mbar_wait(&empty_bar[st], ph ^ 1);
+      mbar_expect_tx(&full_bar[st], L::STAGE_BYTES);
+      tma_load_2d(smem + st * L::STAGE_BYTES + L::A_BYTES, tmB, &full_bar[st], (kb0 + i) * BK, t0.n_blk * BN);
+    }
+    return n;
+  }
+
+  // producer main loop (one lane).  `prefetched` k-blocks (from prefetch_w) already have their barrier armed and W in flight.
+  __device__ __forceinline__ void produce(const CUtensorMap* tmA, const CUtensorMap* tmB, const GemmShape& s, int& kbg,
+                                          int prefetched) const {
+    const int nt = num_tiles(s), kpt = k_per_tile(s);
+    const int kbg0 = kbg;
+    for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+      const TileCoord tc_ = tile_coord(s, tile);
+      const int kb_end = (tc_.split + 1) * kpt;
+      for (int kb = tc_.split * kpt; kb < kb_end; ++kb, ++kbg) {
+        const int st = kbg % STAGES;
+        const uint32_t ph = (kbg / STAGES) & 1;
+        const bool early_b = (kbg - kbg0) < prefetched;
+        if (!early_b) {
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          mbar_expect_tx(&full_bar[st], L::STAGE_BYTES);
         }
-      }
-      griddep_wait();
-      int kbg = 0;  // k-block counter across tiles: ring slot = kbg % STAGES
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord tc_ = tile_coord(s, tile);
-        const int kb_end = (tc_.split + 1) * k_per_tile;
-        for (int kb = tc_.split * k_per_tile; kb < kb_end; ++kb, ++kbg) {
-          const int st = kbg % STAGES;
-          const uint32_t ph = (kbg / STAGES) & 1;
-          const bool early_b = kbg < prefetched;  // this slot's barrier is armed and its W tile already in flight
-          if (!early_b) {
-            mbar_wait(&empty_bar[st], ph ^ 1);
-            mbar_expect_tx(&full_bar[st], L::STAGE_BYTES);
-          }
-          uint8_t* a_dst = smem + st * L::STAGE_BYTES;
-          uint8_t* b_dst = a_dst + L::A_BYTES;
-          if (s.conv) {
-            const int tap = kb / s.kc_blocks;
-            const int kc = kb - tap * s.kc_blocks;
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            tma_load_4d(a_dst, &tmA, &full_bar[st], kc * BK, tc_.w0 + dx, tc_.h0 + dy, tc_.img);
-          } else {
-            tma_load_2d(a_dst, &tmA, &full_bar[st], kb * BK, tc_.m_blk * BM);
-          }
-          if (!early_b) tma_load_2d(b_dst, &tmB, &full_bar[st], kb * BK, tc_.n_blk * BN);
+        uint8_t* a_dst = smem + st * L::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + L::A_BYTES;
+        if (s.conv) {
+          const int tap = kb / s.kc_blocks;
+          const int kc = kb - tap * s.kc_blocks;
+          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+          tma_load_4d(a_dst, tmA, &full_bar[st], kc * BK, tc_.w0 + dx, tc_.h0 + dy, tc_.img);
+        } else {
+          tma_load_2d(a_dst, tmA, &full_bar[st], kb * BK, tc_.m_blk * BM);
         }
+        if (!early_b) tma_load_2d(b_dst, tmB, &full_bar[st], kb * BK, tc_.n_blk * BN);
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-      int kbg = 0, it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_ph = (it >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator stage
+  }
+
+  // MMA issuer main loop (one lane)
+  __device__ __forceinline__ void mma(const GemmShape& s, int& kbg, int& it, long long* trace) const {
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    const int nt = num_tiles(s), kpt = k_per_tile(s);
+    for (int tile = blockIdx.x; tile < nt; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);  // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < kpt; ++kb, ++kbg) {
+        const int st = kbg % STAGES;
+        const uint32_t ph = (kbg / STAGES) & 1;
+        mbar_wait(&full_bar[st], ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < k_per_tile; ++kb, ++kbg) {
-          const int st = kbg % STAGES;
-          const uint32_t ph = (kbg / STAGES) & 1;
-          mbar_wait(&full_bar[st], ph);
-          tc_fence_after();
-          if (trace && kbg == 0) trace[2] = clock64();
-          const uint32_t a_addr = smem_u32(smem + st * L::STAGE_BYTES);
-          const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
-          const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + L::A_BYTES);
+        if (trace && kb == 0 && tile == static_cast<int>(blockIdx.x)) trace[2] = clock64();
+        const uint32_t a_addr = smem_u32(smem + st * L::STAGE_BYTES);
+        const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
+        const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + L::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-          }
-          umma_commit(&empty_bar[st]);  // ring slot reusable once these MMAs have read it
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+          umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator stage complete
-        if (trace) trace[3] = clock64();
+        umma_commit(&empty_bar[st]);  // ring slot reusable once these MMAs have read it
       }
+      umma_commit(&tmem_full_bar[acc]);  // accumulator stage complete
+      if (trace) trace[3] = clock64();
     }
-  } else {
+  }
+
+  // epilogue main loop (warps 2..9, all lanes)
+  template <class Epi>
+  __device__ __forceinline__ void epilogue(const GemmShape& s, const Epi& epi, int& it, long long* trace) const {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3;            // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
     const int half = (warp - 2) >> 2;  // which of the two warps of that quarter: takes 16-column chunks half, half+2, ...
     float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET) + (warp - 2) * STG_FLOATS;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int nt = num_tiles(s);
+    for (int tile = blockIdx.x; tile < nt; tile += gridDim.x, ++it) {
       const TileCoord tc_ = tile_coord(s, tile);
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
-      if (trace && warp == 2 && lane == 0 && it == 0) trace[4] = clock64();
+      if (trace && warp == 2 && lane == 0 && tile == static_cast<int>(blockIdx.x)) trace[4] = clock64();
       const uint32_t t_addr = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
       typename Epi::State st;
       epi.init(st, tc_.split);
@@ -428,10 +441,43 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
       }
     }
   }
+};
+
+template <int BN, int STAGES, class Epi>
+__global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                               const __grid_constant__ CUtensorMap tmB,
+                                                               const GemmShape s, const Epi epi) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  long long* trace = s.trace ? s.trace + static_cast<size_t>(blockIdx.x) * 8 : nullptr;
+  if (trace && threadIdx.x == 0) trace[0] = clock64();
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  Pipe<BN, STAGES> pipe;
+  pipe.setup(smem_raw);
+  if (trace && threadIdx.x == 0) trace[1] = clock64();
+  // PDL: everything above overlapped the predecessor's tail; let our own successor get scheduled early as well
+  griddep_launch_dependents();
+  int kbg = 0, it = 0;
+  if (warp == 0) {
+    if (lane == 0) {
+      // weights never depend on the predecessor kernel: start streaming them before waiting for it
+      const int prefetched = pipe.prefetch_w(&tmB, s, 0);
+      griddep_wait();
+      pipe.produce(&tmA, &tmB, s, kbg, prefetched);
+    }
+  } else if (warp == 1) {
+    griddep_wait();
+    if (lane == 0) pipe.mma(s, kbg, it, trace);
+  } else {
+    griddep_wait();
+    pipe.epilogue(s, epi, it, trace);
+  }
   if (trace && warp == 2 && lane == 0) trace[5] = clock64();
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols<BN>());
+  pipe.teardown();
   if (trace && threadIdx.x == 0) trace[6] = clock64();
 }
 

@@ -126,3 +126,19 @@ def test_beam_search_end_to_end_contract(model, synth_sd, oracle_detail):
     assert ids.shape == ref.shape and ids.dtype == torch.int64
     assert (ids[:, 0] == 50256).all()
     assert (ids.cpu() == ref).float().mean().item() > 0.5
+
+
+def test_megakernel_step_matches_multi_kernel_step(model, oracle_detail):
+    """The persistent one-kernel decode step and the multi-kernel (CUDA graph + PDL) step run the same arithmetic in the
+    same order: greedy tokens must be identical."""
+    eng = model._engine()
+    feats = oracle_detail["sel_feats"].contiguous().cuda()
+    eng.set_option("megakernel", 0)
+    a = eng.lm_generate(feats, 12)
+    eng.set_option("megakernel", 1)
+    b = eng.lm_generate(feats, 12)
+    c = eng.lm_generate(feats[:5], 7)  # different row count: parameters are rebuilt
+    eng.set_option("megakernel", 0)
+    d = eng.lm_generate(feats[:5], 7)
+    assert np.array_equal(a, b)
+    assert np.array_equal(c, d)

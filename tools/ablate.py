@@ -26,6 +26,16 @@ def run(mask, pdl=1, graph=1):
 
 base = run(0)
 print("full step                : %.3f ms" % base, flush=True)
+eng.set_option("megakernel", 1)
+print("full step, megakernel    : %.3f ms" % run(0), flush=True)
+import numpy as np
+tr = eng.debug_read("mega_trace", (256,), np.int64).astype(np.float64)
+d = np.diff(tr[:172]) / 1.965e3
+names = ["LN1+prefetch", "c_attn", "attention", "proj", "LN2", "c_fc", "mproj"]
+per = d[:168].reshape(24, 7)
+print("megakernel phase durations (us, CTA 0, last step, mean over 24 layers):", {n: round(float(per[:, i].mean()), 2) for i, n in enumerate(names)}, flush=True)
+print("  layer 1 phases:", [round(float(v), 2) for v in per[1]], " tail (LNf, lm_head, greedy):", [round(float(v), 2) for v in d[168:171]], flush=True)
+eng.set_option("megakernel", 0)
 print("full step, PDL off       : %.3f ms" % run(0, pdl=0), flush=True)
 print("full step, eager no graph: %.3f ms" % run(0, graph=0), flush=True)
 configs = [("attention", 1), ("layernorm", 2), ("c_attn", 4), ("attn_c_proj", 8), ("mlp_c_fc", 16), ("mlp_c_proj", 32),
