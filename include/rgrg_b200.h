@@ -82,6 +82,12 @@ RGRG_API int rgrg_detect(rgrg_engine_t* e, const float* images, int images_on_ho
                 uint8_t* out_detected, float* out_boxes, float* out_scores, float* out_region_features,
                 int32_t* out_top_idx, int32_t* out_num_proposals, int* out_R, void* stream);
 
+/* replaces: get_bbox_features(model, images, bbox_coordinates) (evaluate_bbox_variations.py:92-110): user boxes -> backbone ->
+ * RoIAlign 8x8 -> AvgPool(8) -> dim_reduction.  boxes host fp32 [B,29,4] (x1,y1,x2,y2 in pixels);
+ * out_features host fp32 [B*29,1024], the input of rgrg_lm_generate (the "always 29 rows per image" mode). */
+RGRG_API int rgrg_bbox_features(rgrg_engine_t* e, const float* images, int images_on_host, int B, int S, const float* boxes_host,
+                       float* out_features_host, void* stream);
+
 /* ---- stage-level entry points (teacher-forced parity tests and the roofline harness call these) ---------------- */
 
 /* decoder logits with forced tokens: forced_ids int32 dev [R, n_tokens]; out_logits fp32 dev [n_tokens, R, 50257]
@@ -137,7 +143,7 @@ RGRG_API int rgrg_backbone(rgrg_engine_t* e, const float* images_dev, int B, int
 RGRG_API int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst, size_t bytes);
 
 /* behaviour switches: "implicit_conv" (0/1), "cuda_graph" (0/1), "gemm_impl" (0 tcgen05, 2 CUDA-core cross-check),
- * "megakernel" (0/1: greedy decode step as one persistent cooperative kernel), "pdl" (0/1: programmatic dependent launch between the kernels of a decode step), "profile" (0/1: record CUDA events around every kernel category on the launch stream; disables graph replay) */
+ * "dual" (0/1: greedy decode step as two concurrent row halves), "megakernel" (0/1: greedy decode step as one persistent cooperative kernel), "pdl" (0/1: programmatic dependent launch between the kernels of a decode step), "profile" (0/1: record CUDA events around every kernel category on the launch stream; disables graph replay) */
 RGRG_API int rgrg_set_option(rgrg_engine_t* e, const char* key, int value);
 
 /* per-category device time since "profile" was switched on: text lines "<category> <total ms> <launches>\n" */

@@ -45,6 +45,19 @@ def main():
     from torchvision.models.detection.rpn import concat_box_prediction_layers
 
     imgs = synth.synthetic_images(2, 512, seed=1001)
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+
+    # ---- selection-based entry: user boxes -> region features (evaluate_bbox_variations.py:92-110), run on the reference's modules
+    g = torch.Generator().manual_seed(77)
+    ctr = torch.rand(2, 29, 2, generator=g) * 300 + 100
+    wh = torch.rand(2, 29, 2, generator=g) * 160 + 40
+    user_boxes = [torch.cat([(ctr[b] - wh[b] / 2).clamp(0, 512), (ctr[b] + wh[b] / 2).clamp(0, 512)], dim=1) for b in range(2)]
+    f_ = det.backbone(imgs)
+    maps = det.roi_heads.box_roi_pool({"0": f_}, user_boxes, [(512, 512)] * 2)
+    bbox_feats = det.roi_heads.dim_reduction(torch.squeeze(det.roi_heads.avg_pool(maps)))
+    npz("bbox_features.npz", boxes=torch.stack(user_boxes), features=bbox_feats)
+    if only == "bbox":
+        return
 
     # ---- anchors (torchvision AnchorGenerator as configured at object_detector.py:78-83)
     feats = det.backbone(imgs)

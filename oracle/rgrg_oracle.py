@@ -9,9 +9,9 @@ arithmetic the reference reaches (torchvision 0.13.1 detection utilities, HF GPT
 published algorithm; torch CPU ops (conv2d, linear, softmax ...) are used as plain fp32 arithmetic.
 
 PINNING.  The reference has no tests, golden vectors or fixtures, so the oracle is pinned against
-outputs of the reference itself run in the build container: tests/test_oracle_vs_reference.py imports the unmodified
-reference through oracle/ref_harness.py and compares stage by stage, and oracle/make_golden.py commits
-reference-generated vectors under tests/golden/.  Beam search rests on oracle/beam_scorer.py, whose upstream
+outputs of the reference itself run in the build container: oracle/make_golden.py imports the unmodified reference
+through oracle/ref_harness.py and commits its stage inputs / outputs under tests/golden/; tests/test_oracle_golden.py
+checks this file against every one of them.  Beam search rests on oracle/beam_scorer.py, whose upstream
 (transformers==4.19.2 BeamSearchScorer) is not vendored: beam parity is "unpinned" beyond the reference's own call
 sites.
 
@@ -527,6 +527,18 @@ def detect(sd: SD, images: torch.Tensor, detail: Optional[dict] = None) -> dict:
     if detail is not None:
         detail.update(features=feats, proposals=proposals, rpn=rpn_detail, roi=roi_detail)
     return out
+
+
+@torch.no_grad()
+def bbox_features(sd: SD, images: torch.Tensor, bbox_coordinates: List[torch.Tensor]) -> torch.Tensor:
+    """evaluate_bbox_variations.py:92-110 `get_bbox_features`: user boxes (29 per image) -> RoIAlign -> AvgPool(8) ->
+    dim_reduction -> [(B*29), 1024]; the caller then runs `language_model.generate` on every row (:131-136)."""
+    S = images.shape[-1]
+    feats = backbone(sd, images)
+    pooled = box_roi_pool(feats, bbox_coordinates, S)
+    f = F.avg_pool2d(pooled, 8).reshape(pooled.shape[0], -1)
+    rh = "object_detector.roi_heads.dim_reduction"
+    return F.linear(f, sd[rh + ".weight"], sd[rh + ".bias"])
 
 
 @torch.no_grad()

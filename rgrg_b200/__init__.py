@@ -6,6 +6,6 @@ Nothing here falls back to PyTorch or the CPU: without the built library the eng
 """
 from . import _cabi  # noqa: F401
 from .engine import Engine  # noqa: F401
-from .model import LanguageModel, ReportGenerationModel  # noqa: F401
+from .model import LanguageModel, ReportGenerationModel, get_bbox_features  # noqa: F401
 
-__all__ = ["Engine", "ReportGenerationModel", "LanguageModel"]
+__all__ = ["Engine", "ReportGenerationModel", "LanguageModel", "get_bbox_features"]

@@ -230,6 +230,7 @@ struct GreedyState {
   int* unfinished;   // [rows] 1 = still generating
   int* unfinished_count;  // [max_steps], zeroed by greedy_init_kernel
   int* ticket;       // CTA arrival counter of greedy_update_kernel
+  int advance;       // 1: the last CTA of greedy_update_kernel publishes step + 1 (0 when two halves run concurrently)
   int* step_ptr;
   const int* forced; // optional [rows, ids_ld]: teacher forcing — ids[:, t+1] = forced[:, t+1], arg-max is only recorded
   int* argmax_out;   // optional [max_steps, rows] raw arg-max per step (tests)
@@ -290,16 +291,24 @@ __global__ void __launch_bounds__(256) greedy_update_kernel(const float* __restr
     const int ticket = atomicAdd(g.ticket, 1);
     if (ticket == static_cast<int>(gridDim.x) - 1) {
       *g.ticket = 0;
-      *g.step_ptr = t + 1;
+      if (g.advance) *g.step_ptr = t + 1;
     }
   }
+}
+
+__global__ void step_advance_kernel(int* step_ptr) {
+  if (threadIdx.x == 0) *step_ptr += 1;
 }
 
 // start of a generate() call: ids[:, 0] = BOS, unfinished = 1, step = 0
 __global__ void greedy_init_kernel(GreedyState g, int rows) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < g.ids_ld) g.unfinished_count[r] = 0;
-  if (r == 0) *g.ticket = 0;
+  if (r == 0) {
+    g.ticket[0] = 0;
+    g.ticket[1] = 0;
+    g.ticket[2] = 0;
+  }
   if (r < rows) {
     g.ids[static_cast<size_t>(r) * g.ids_ld] = g.forced ? g.forced[static_cast<size_t>(r) * g.ids_ld] : EOS_ID;
     g.unfinished[r] = 1;

@@ -171,6 +171,7 @@ struct rgrg_engine {
   int opt_cuda_graph = 1;
   int opt_gemm_impl = 0;
   int opt_pdl = 1;
+  int opt_dual = 0;        // greedy decode step as two concurrent row halves (two streams inside the step graph)
   int opt_megakernel = 0;  // greedy decode step as ONE persistent cooperative kernel (decoder_megakernel.cuh)
   int opt_ablate = 0;  // tuning only: bit mask of decode-step kernels to skip (results become meaningless, timing attributes cost)
   bool pdl_now = false;  // set while the decode step is being issued: its kernels carry the PDL launch attribute
@@ -211,6 +212,9 @@ struct rgrg_engine {
     for (auto& g : step_graphs) cudaGraphExecDestroy(g.second);
     for (cudaEvent_t ev : prof_pool) cudaEventDestroy(ev);
     if (ev_enter) cudaEventDestroy(ev_enter);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side_stream) cudaStreamDestroy(side_stream);
     if (own_stream) cudaStreamDestroy(own_stream);
     for (void* p : weight_allocs) cudaFree(p);
     DevBuf* all[] = {&images, &act[0], &act[1], &t1, &t2, &idb, &sub, &col, &feats, &rpn_t, &rpn_out, &prop_boxes,
@@ -864,20 +868,47 @@ struct rgrg_engine {
     gemm("lm_image_kv", img.as<bf16>(), R, ukv, e, st, true);
   }
 
-  // transformer body of one decode step for `rows` rows (embedding .. final LayerNorm); every kernel reads the step
-  // index from device memory.  Leaves ln_f(h) as bf16 in `x`.
-  void decode_forward(int rows, const int* ids_ptr, int ids_ld, cudaStream_t st) {
+  // a contiguous row range of the decoder workspace (the whole batch, or one of the two concurrent halves)
+  struct DecView {
+    int rows;
+    float* h;
+    bf16 *x, *q, *attn_o, *mid;
+    float* parts;
+    KvGeom kv;
+    float* part_val;
+    int* part_idx;
+  };
+  DecView dec_view(int row0, int rows) {
+    DecView v;
+    v.rows = rows;
+    v.h = h.as<float>() + static_cast<size_t>(row0) * DM;
+    v.x = x.as<bf16>() + static_cast<size_t>(row0) * DM;
+    v.q = q.as<bf16>() + static_cast<size_t>(row0) * DM;
+    v.attn_o = attn_o.as<bf16>() + static_cast<size_t>(row0) * DM;
+    v.mid = mlp_mid.as<bf16>() + static_cast<size_t>(row0) * 4 * DM;
+    v.parts = splitk_parts.as<float>() + static_cast<size_t>(row0) * DM * 4;
+    v.kv = kv_geom();
+    v.kv.cache += static_cast<size_t>(row0) * 16 * ws_slots * 64;  // KvGeom::offset is linear in the row index
+    v.part_val = part_val.as<float>() + static_cast<size_t>(row0) * 2048;
+    v.part_idx = part_idx.as<int>() + static_cast<size_t>(row0) * 2048;
+    return v;
+  }
+
+  // transformer body of one decode step for the rows of `v` (embedding .. final LayerNorm); every kernel reads the step
+  // index from device memory.  Leaves ln_f(h) as bf16 in v.x.  ids_ptr points at the first row of the view.
+  void decode_forward(const DecView& v, const int* ids_ptr, int ids_ld, cudaStream_t st) {
+    const int rows = v.rows;
     const int* sp = step.as<int>();
     {
       ProfScope ps(this, "embed", st);
-      launch_kernel(dec::embed_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, st, false, wte_f32, ids_ptr, ids_ld, sp, h.as<float>(), rows);
+      launch_kernel(dec::embed_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, st, false, wte_f32, ids_ptr, ids_ld, sp, v.h, rows);
       ++launches;
     }
     pdl_now = opt_pdl != 0;
     const int ln_grid = ceil_div(rows, 8);
     constexpr int SPLITS = 4;
     const size_t pstride = static_cast<size_t>(rows) * DM;
-    float* parts = splitk_parts.as<float>();
+    float* parts = v.parts;
     // LayerNorm fused with the residual update of the preceding split-K projection (pending_bias != null)
     const float* pending_bias = nullptr;
     auto ln = [&](const float* g, const float* b) {
@@ -887,58 +918,103 @@ struct rgrg_engine {
         return;
       }
       if (pending_bias)
-        launch_kernel(dec::layernorm_kernel<SPLITS>, dim3(ln_grid), dim3(256), 0, st, pdl_now, h.as<float>(), g, b, x.as<bf16>(), rows,
-                      parts, pstride, pending_bias);
+        launch_kernel(dec::layernorm_kernel<SPLITS>, dim3(ln_grid), dim3(256), 0, st, pdl_now, v.h, g, b, v.x, rows, parts, pstride,
+                      pending_bias);
       else
-        launch_kernel(dec::layernorm_kernel<0>, dim3(ln_grid), dim3(256), 0, st, pdl_now, h.as<float>(), g, b, x.as<bf16>(), rows,
-                      parts, pstride, pending_bias);
+        launch_kernel(dec::layernorm_kernel<0>, dim3(ln_grid), dim3(256), 0, st, pdl_now, v.h, g, b, v.x, rows, parts, pstride,
+                      pending_bias);
       ++launches;
       pending_bias = nullptr;
     };
     for (int l = 0; l < NLAYER; ++l) {
       const LayerW& L = layers[l];
       ln(L.ln1_g, L.ln1_b);
-      EpiQkvAppend eq{q.as<bf16>(), L.attn.bias, kv_geom(), l, sp};
-      if (!(opt_ablate & 4)) gemm("c_attn", x.as<bf16>(), rows, L.attn, eq, st, true);
+      EpiQkvAppend eq{v.q, L.attn.bias, v.kv, l, sp};
+      if (!(opt_ablate & 4)) gemm("c_attn", v.x, rows, L.attn, eq, st, true);
       if (!(opt_ablate & 1)) {
         ProfScope ps(this, "attention", st);
-        launch_kernel(dec::attention_kernel, dim3(ceil_div(rows * 16, 4)), dim3(128), 0, st, pdl_now, q.as<bf16>(), kv_geom(), l, sp,
-                      attn_o.as<bf16>(), rows, beam_anc, beam_slots, beam_nb);
+        launch_kernel(dec::attention_kernel, dim3(ceil_div(rows * 16, 4)), dim3(128), 0, st, pdl_now, v.q, v.kv, l, sp, v.attn_o, rows,
+                      beam_anc, beam_slots, beam_nb);
         ++launches;
       }
-      if (!(opt_ablate & 8)) gemm_splitk("attn_c_proj", attn_o.as<bf16>(), rows, L.proj, parts, SPLITS, st);
+      if (!(opt_ablate & 8)) gemm_splitk("attn_c_proj", v.attn_o, rows, L.proj, parts, SPLITS, st);
       pending_bias = L.proj.bias;
       ln(L.ln2_g, L.ln2_b);
       if (!(opt_ablate & 16))
-        gemm("mlp_c_fc", x.as<bf16>(), rows, L.fc, epi<true, ACT_GELU_NEW, RES_NONE, true>(mlp_mid.p, L.fc.bias, 4 * DM), st, true);
-      if (!(opt_ablate & 32)) gemm_splitk("mlp_c_proj", mlp_mid.as<bf16>(), rows, L.mproj, parts, SPLITS, st);
+        gemm("mlp_c_fc", v.x, rows, L.fc, epi<true, ACT_GELU_NEW, RES_NONE, true>(v.mid, L.fc.bias, 4 * DM), st, true);
+      if (!(opt_ablate & 32)) gemm_splitk("mlp_c_proj", v.mid, rows, L.mproj, parts, SPLITS, st);
       pending_bias = L.mproj.bias;
     }
     ln(lnf_g, lnf_b);
   }
   void end_pdl() { pdl_now = false; }
 
-  // one greedy decode step.  logits_out != null: lm_head stores fp32 logits there instead of the fused arg-max.
-  int decode_step(int rows, const dec::GreedyState& g, float* logits_out, cudaStream_t st) {
-    const int before = static_cast<int>(launches);
-    decode_forward(rows, g.ids, g.ids_ld, st);
+  // lm_head + greedy bookkeeping for one view.  logits_out != null: lm_head stores fp32 logits there instead of the
+  // fused arg-max.  `g` must already point at the view's first row.
+  void decode_head(const DecView& v, const dec::GreedyState& g, float* logits_out, cudaStream_t st) {
+    const int rows = v.rows;
     if (logits_out || opt_gemm_impl == 2) {
       float* dst = logits_out ? logits_out : logits_tmp.as<float>();
-      gemm("lm_head", x.as<bf16>(), rows, lm_head, epi<false, ACT_NONE, RES_NONE, false>(dst, nullptr, VOCAB), st, true);
+      gemm("lm_head", v.x, rows, lm_head, epi<false, ACT_NONE, RES_NONE, false>(dst, nullptr, VOCAB), st, true);
       ProfScope ps(this, "greedy_update", st);
       launch_kernel(dec::greedy_update_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, st, pdl_now, static_cast<const float*>(nullptr),
                     static_cast<const int*>(nullptr), 0, static_cast<const float*>(dst), g, rows);
     } else {
       const int bn = pick_bn(ceil_div(rows, tc::BM), VOCAB);
       const int n_tiles = 2 * ceil_div(VOCAB, bn);  // two partials per tile: one per epilogue warp of a lane quarter
-      EpiArgmaxPartial ea{part_val.as<float>(), part_idx.as<int>(), n_tiles};
-      gemm("lm_head", x.as<bf16>(), rows, lm_head, ea, st, true, bn);
+      EpiArgmaxPartial ea{v.part_val, v.part_idx, n_tiles};
+      gemm("lm_head", v.x, rows, lm_head, ea, st, true, bn);
       ProfScope ps(this, "greedy_update", st);
       launch_kernel(dec::greedy_update_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, st, pdl_now,
-                    static_cast<const float*>(part_val.as<float>()), static_cast<const int*>(part_idx.as<int>()), n_tiles,
+                    static_cast<const float*>(v.part_val), static_cast<const int*>(v.part_idx), n_tiles,
                     static_cast<const float*>(nullptr), g, rows);
     }
     end_pdl();
+    ++launches;
+  }
+
+  // one greedy decode step over all rows, single chain
+  int decode_step(int rows, const dec::GreedyState& g, float* logits_out, cudaStream_t st) {
+    const int before = static_cast<int>(launches);
+    DecView v = dec_view(0, rows);
+    decode_forward(v, g.ids, g.ids_ld, st);
+    decode_head(v, g, logits_out, st);
+    return static_cast<int>(launches) - before;
+  }
+
+  // one greedy decode step as TWO independent row halves on two streams: decode rows never interact, and the kernels
+  // of a half are latency-bound (profiles/r01_decode_ablation.md), so the halves overlap each other's launch / ramp /
+  // drain bubbles and one half's HBM-bound attention runs beside the other half's tensor-core GEMMs.
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int decode_step_dual(int rows, const dec::GreedyState& g, cudaStream_t st) {
+    const int before = static_cast<int>(launches);
+    if (!side_stream) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    int rows_a = ((rows / 2 + 127) / 128) * 128;  // split on an M-tile boundary: no extra tile padding
+    if (rows_a >= rows) rows_a = rows / 2;
+    const int rows_b = rows - rows_a;
+    CUDA_CHECK(cudaEventRecord(ev_fork, st));
+    CUDA_CHECK(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+    for (int b = 0; b < 2; ++b) {
+      const int row0 = b ? rows_a : 0;
+      cudaStream_t s = b ? side_stream : st;
+      DecView v = dec_view(row0, b ? rows_b : rows_a);
+      dec::GreedyState gb = g;
+      gb.ids = g.ids + static_cast<size_t>(row0) * g.ids_ld;
+      gb.unfinished = g.unfinished + row0;
+      gb.ticket = g.ticket + 1 + b;
+      gb.advance = 0;
+      decode_forward(v, gb.ids, gb.ids_ld, s);
+      decode_head(v, gb, nullptr, s);
+    }
+    CUDA_CHECK(cudaEventRecord(ev_join, side_stream));
+    CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
+    dec::step_advance_kernel<<<1, 32, 0, st>>>(g.step_ptr);
+    KERNEL_CHECK();
     ++launches;
     return static_cast<int>(launches) - before;
   }
@@ -1084,7 +1160,8 @@ struct rgrg_engine {
     beam_nb = nb;
     for (int t = 0; t < steps; ++t) {
       beam_anc = s.anc[cur];
-      decode_forward(rows, s.ids[cur], max_length, st);
+      DecView v = dec_view(0, rows);
+      decode_forward(v, s.ids[cur], max_length, st);
       gemm("lm_head", x.as<bf16>(), rows, lm_head, epi<false, ACT_NONE, RES_NONE, false>(logits_tmp.p, nullptr, VOCAB), st, true);
       end_pdl();
       beam_bookkeeping(s, logits_tmp.as<float>(), R, cur, st);
@@ -1203,13 +1280,14 @@ struct rgrg_engine {
     g.unfinished_count = unf_count.as<int>();
     g.step_ptr = step.as<int>();
     g.ticket = step.as<int>() + 1;
+    g.advance = 1;
     dec::greedy_init_kernel<<<ceil_div(std::max(R, max_length), 256), 256, 0, st>>>(g, R);
     KERNEL_CHECK();
     ++launches;
     const int steps = max_length - 1;
     cudaGraphExec_t exec = nullptr;
     int nodes = 0;
-    const int graph_key = R * 4096 + max_length;
+    const int graph_key = (R * 4096 + max_length) * 2 + (opt_dual ? 1 : 0);
     const bool use_mega = opt_megakernel && opt_gemm_impl != 2 && !opt_ablate;
     if (use_mega) {
       mega_prepare(R, g);
@@ -1218,6 +1296,7 @@ struct rgrg_engine {
       // step 0 always runs eagerly (it also makes sure every kernel is loaded and configured before a capture)
       decode_step(R, g, nullptr, st);
     }
+    const bool use_dual = opt_dual && !use_mega && opt_gemm_impl != 2 && R >= 256;
     if (!use_mega && opt_cuda_graph && !prof_on && steps > 1) {
       auto it = step_graphs.find(graph_key);
       if (it == step_graphs.end()) {
@@ -1225,7 +1304,7 @@ struct rgrg_engine {
         const int64_t saved = launches;
         CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         try {
-          nodes = decode_step(R, g, nullptr, st);
+          nodes = use_dual ? decode_step_dual(R, g, st) : decode_step(R, g, nullptr, st);
         } catch (...) {
           cudaGraph_t dead;
           cudaStreamEndCapture(st, &dead);
@@ -1250,6 +1329,8 @@ struct rgrg_engine {
       } else if (exec) {
         CUDA_CHECK(cudaGraphLaunch(exec, st));
         launches += nodes;
+      } else if (use_dual) {
+        decode_step_dual(R, g, st);
       } else {
         decode_step(R, g, nullptr, st);
       }
@@ -1372,6 +1453,7 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "gemm_impl") e->opt_gemm_impl = value;
   else if (k == "pdl") e->opt_pdl = value;
   else if (k == "megakernel") e->opt_megakernel = value;
+  else if (k == "dual") e->opt_dual = value;
   else if (k == "ablate") {
     e->opt_ablate = value;
     for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.second);
@@ -1483,6 +1565,39 @@ int rgrg_lm_generate(rgrg_engine_t* e, const float* feats, int feats_on_host, in
   });
 }
 
+int rgrg_bbox_features(rgrg_engine_t* e, const float* images, int images_on_host, int B, int S, const float* boxes_host,
+                       float* out_features_host, void* stream) {
+  RGRG_TRY(e, {
+    check_ready(e);
+    cudaStream_t st = e->enter(stream);
+    const float* img = stage_images(e, images, images_on_host, B, S, st);
+    e->ensure_detector_ws(B, S);
+    const int f = S / 32;
+    e->run_backbone(img, B, S, e->feats.as<bf16>(), st);
+    // the 29 user boxes of image b occupy proposal slots 0..28; region c uses slot c
+    std::vector<float> slots(static_cast<size_t>(B) * TOPK * 4, 0.0f);
+    std::vector<int> cnt(B, NREG), idx(static_cast<size_t>(B) * NREG);
+    for (int b = 0; b < B; ++b)
+      for (int c = 0; c < NREG; ++c) {
+        memcpy(&slots[(static_cast<size_t>(b) * TOPK + c) * 4], boxes_host + (static_cast<size_t>(b) * NREG + c) * 4, 16);
+        idx[b * NREG + c] = c;
+      }
+    CUDA_CHECK(cudaMemcpyAsync(e->prop_boxes.p, slots.data(), slots.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(e->prop_count.p, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(e->top_idx.p, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, st));
+    const float scale = exp2f(roundf(log2f(static_cast<float>(f) / static_cast<float>(S))));
+    det::roi_mean_kernel<<<dim3(NREG, B), 256, 0, st>>>(e->feats.as<bf16>(), e->prop_boxes.as<float>(), e->prop_count.as<int>(),
+                                                        e->top_idx.as<int>(), e->mean2048.as<float>(), f, 2048, scale);
+    KERNEL_CHECK();
+    const int rows = B * NREG;
+    e->simt_f32(e->mean2048.as<float>(), e->dimred.w, rows, 1024, 2048,
+                rgrg_engine::epi<false, ACT_NONE, RES_NONE, true>(e->trf.p, e->dimred.bias, 1024), st);
+    e->launches += 2;
+    CUDA_CHECK(cudaMemcpyAsync(out_features_host, e->trf.p, static_cast<size_t>(rows) * 1024 * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));  // `slots`, `cnt`, `idx` must outlive the copies
+  });
+}
+
 int rgrg_lm_forced_logits(rgrg_engine_t* e, const float* feats_dev, int R, const int32_t* forced_ids_dev, int n_tokens,
                           float* out_logits_dev, void* stream) {
   RGRG_TRY(e, {
@@ -1498,6 +1613,7 @@ int rgrg_lm_forced_logits(rgrg_engine_t* e, const float* feats_dev, int R, const
     g.unfinished_count = e->unf_count.as<int>();
     g.step_ptr = e->step.as<int>();
     g.ticket = e->step.as<int>() + 1;
+    g.advance = 1;
     g.forced = forced_ids_dev;
     dec::greedy_init_kernel<<<ceil_div(std::max(R, n_tokens), 256), 256, 0, st>>>(g, R);
     KERNEL_CHECK();

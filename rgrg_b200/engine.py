@@ -128,6 +128,19 @@ class Engine:
         return {"selected": sel.astype(bool), "detected": det.astype(bool), "boxes": boxes, "scores": scores,
                 "region_features": trf, "top_idx": top_idx, "num_proposals": nprop, "R": R.value}
 
+    def bbox_features(self, images: torch.Tensor, boxes) -> np.ndarray:
+        """boxes: [B,29,4] (tensor / array / list of 29x4 tensors) -> fp32 [B*29, 1024]"""
+        B, S = int(images.shape[0]), int(images.shape[-1])
+        on_host = images.device.type == "cpu"
+        images = images.to(torch.float32).contiguous()
+        if isinstance(boxes, (list, tuple)):
+            boxes = torch.stack([b.detach().to("cpu", torch.float32) for b in boxes])
+        boxes = np.ascontiguousarray(torch.as_tensor(boxes).detach().to("cpu", torch.float32).numpy().reshape(B, NUM_REGIONS, 4))
+        out = np.zeros((B * NUM_REGIONS, 1024), dtype=np.float32)
+        self._check(self._lib.rgrg_bbox_features(self._h, _ptr(images), int(on_host), B, S, _ptr(boxes), _ptr(out),
+                                                 _stream(self.device)))
+        return out
+
     # ---- stage-level (tests / roofline harness); all tensors are CUDA tensors on self.device
     def lm_forced_logits(self, feats: torch.Tensor, forced_ids: torch.Tensor) -> torch.Tensor:
         R, n = int(forced_ids.shape[0]), int(forced_ids.shape[1])

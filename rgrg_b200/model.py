@@ -65,6 +65,14 @@ class LanguageModel:
         return torch.from_numpy(ids.astype(np.int64)).to(self._owner.device)
 
 
+def get_bbox_features(model: "ReportGenerationModel", images, bbox_coordinates) -> torch.Tensor:
+    """Drop-in for evaluate_bbox_variations.py:92-110 `get_bbox_features(model, images, bbox_coordinates)`:
+    bbox_coordinates is a list (len = batch) of [29,4] tensors; returns [(batch*29), 1024] region features that
+    `model.language_model.generate` turns into one sentence per box (:131-136)."""
+    feats = model._engine().bbox_features(images, bbox_coordinates)
+    return torch.from_numpy(feats).to(model.device)
+
+
 class ReportGenerationModel:
     def __init__(self, pretrain_without_lm_model: bool = False, device: Optional[torch.device] = None):
         self.pretrain_without_lm_model = pretrain_without_lm_model

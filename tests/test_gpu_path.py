@@ -142,3 +142,31 @@ def test_megakernel_step_matches_multi_kernel_step(model, oracle_detail):
     d = eng.lm_generate(feats[:5], 7)
     assert np.array_equal(a, b)
     assert np.array_equal(c, d)
+
+
+def test_dual_half_step_matches_single_chain(model, oracle_detail):
+    """Two concurrent row halves (two streams in the step graph) vs one chain: rows never interact, tokens identical."""
+    eng = model._engine()
+    feats = torch.cat([oracle_detail["sel_feats"]] * 6, 0).contiguous().cuda()  # 348 rows >= the 256-row threshold
+    eng.set_option("dual", 0)
+    a = eng.lm_generate(feats, 10)
+    eng.set_option("dual", 1)
+    b = eng.lm_generate(feats, 10)
+    eng.set_option("cuda_graph", 0)
+    c = eng.lm_generate(feats, 10)
+    eng.set_option("cuda_graph", 1)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_bbox_features_entry(model, synth_sd, images, golden):
+    """n1: user boxes -> region features -> one sentence per box (always 29 rows per image)."""
+    from rgrg_b200 import get_bbox_features
+
+    g = golden("bbox_features.npz")
+    boxes = [torch.from_numpy(g["boxes"][0]), torch.from_numpy(g["boxes"][1])]
+    ref = O.bbox_features(synth_sd, images, boxes)
+    feats = get_bbox_features(model, images.cuda(), [b.cuda() for b in boxes])
+    assert feats.shape == (58, 1024)
+    assert _rel(feats.cpu(), ref) < 0.05  # bf16 backbone
+    ids = model.language_model.generate(feats, max_length=5)
+    assert ids.shape == (58, 5)

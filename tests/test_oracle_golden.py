@@ -116,3 +116,15 @@ def test_whole_path_matches_reference(golden, synth_sd):
         assert torch.equal(det["top_scores"], T(g["top_scores"]))
     else:
         assert ids.shape == g["ids"].shape
+
+
+def test_bbox_features_match_reference(golden, synth_sd):
+    """Selection-based entry (evaluate_bbox_variations.py:92-110).  Depends on the BN-calibrated backbone: exact on the
+    host that generated the fixture, tolerance elsewhere."""
+    from rgrg_b200 import synth
+
+    g = golden("bbox_features.npz")
+    imgs = synth.synthetic_images(2, 512, seed=1001)
+    feats = O.bbox_features(synth_sd, imgs, [T(g["boxes"][0]), T(g["boxes"][1])])
+    assert feats.shape == (58, 1024)
+    assert torch.allclose(feats, T(g["features"]), rtol=1e-3, atol=1e-3)

@@ -24,9 +24,12 @@ def run(mask, pdl=1, graph=1):
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / n / (T - 1) * 1e3  # ms per decode step
 
+eng.set_option("dual", 1)
+print("full step, dual halves   : %.3f ms" % run(0), flush=True)
+eng.set_option("dual", 0)
 base = run(0)
 print("full step                : %.3f ms" % base, flush=True)
-eng.set_option("megakernel", 1)
+eng.set_option("megakernel", 1 if "mega" in sys.argv else 0)
 print("full step, megakernel    : %.3f ms" % run(0), flush=True)
 import numpy as np
 tr = eng.debug_read("mega_trace", (256,), np.int64).astype(np.float64)
