@@ -41,34 +41,48 @@ struct Params {
   int* part_idx;
   int n_parts;
   int rows;
-  unsigned* sync_counter;  // zeroed by the host before every launch
+  unsigned* sync_counter;  // [64] (arrival counter + release flag on separate lines), zeroed by the host before every launch
   long long* trace;        // optional [256]: clock64 of CTA 0 after every grid barrier (tuning)
 };
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-// all CTAs of the (co-resident) grid
+// Barrier over all CTAs of the (co-resident) grid.  counter[0] counts arrivals (monotonic within a launch), counter[32]
+// (a different 128-byte line) is the release flag: the last arriver of generation g publishes g there, everybody else
+// polls that read-mostly line instead of hammering the line the atomics go to.
 __device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& gen) {
   fence_proxy_async();
   __syncthreads();
   if (threadIdx.x == 0) {
     ++gen;
-    const unsigned target = gen * gridDim.x;
-    __threadfence();
-    atomicAdd(counter, 1u);
-    long long start = clock64();
-    unsigned v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-      if (v < target && clock64() - start > 4000000000LL) {
-        printf("rgrg_b200: grid barrier timed out (block %d, gen %u, count %u)\n", blockIdx.x, gen, v);
-        __trap();
+    unsigned* flag = counter + 32;
+    unsigned old;
+    // release: everything this CTA wrote (ordered before by bar.sync) is visible before the arrival is
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(counter) : "memory");
+    if (old == gen * gridDim.x - 1) {
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(gen) : "memory");
+    } else {
+      long long start = clock64();
+      unsigned v;
+      for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= gen) break;
+        if (clock64() - start > 4000000000LL) {
+          printf("rgrg_b200: grid barrier timed out (block %d, gen %u, flag %u)\n", blockIdx.x, gen, v);
+          __trap();
+        }
       }
-    } while (v < target);
-    __threadfence();
+    }
   }
   __syncthreads();
   fence_proxy_async();
+}
+// tuning: cost of one barrier
+__global__ void __launch_bounds__(tc::NUM_THREADS, 1) grid_sync_bench_kernel(unsigned* counter, int iters, long long* out) {
+  unsigned gen = 0;
+  const long long t0 = clock64();
+  for (int i = 0; i < iters; ++i) grid_sync(counter, gen);
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = clock64() - t0;
 }
 __device__ __forceinline__ void mark(long long* trace, int& idx) {
   if (trace && blockIdx.x == 0 && threadIdx.x == 0) trace[idx] = clock64();

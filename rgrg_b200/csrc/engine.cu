@@ -1233,9 +1233,9 @@ struct rgrg_engine {
     hp->part_idx = part_idx.as<int>();
     hp->n_parts = 2 * ceil_div(VOCAB, mega::BN);
     hp->rows = rows;
-    mega_sync.ensure(64 + 256 * 8);
+    mega_sync.ensure(256 + 256 * 8);
     hp->sync_counter = mega_sync.as<unsigned>();
-    hp->trace = reinterpret_cast<long long*>(static_cast<char*>(mega_sync.p) + 64);
+    hp->trace = reinterpret_cast<long long*>(static_cast<char*>(mega_sync.p) + 256);
     mega_params.ensure(sizeof(mega::Params));
     cudaError_t err = cudaMemcpy(mega_params.p, hp, sizeof(mega::Params), cudaMemcpyHostToDevice);
     delete hp;
@@ -1251,7 +1251,7 @@ struct rgrg_engine {
   }
   int decode_step_mega(int rows, cudaStream_t st) {
     ProfScope ps(this, "decoder_step_megakernel", st);
-    CUDA_CHECK(cudaMemsetAsync(mega_sync.p, 0, 4, st));
+    CUDA_CHECK(cudaMemsetAsync(mega_sync.p, 0, 256, st));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(tc::num_sms());
     cfg.blockDim = dim3(tc::NUM_THREADS);
@@ -1841,10 +1841,32 @@ int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst, size_t b
     else if (n == "selection_logits") b = &e->sel_logits;
     else if (n == "region_features_2048") b = &e->mean2048;
     else if (n == "fc7") b = &e->f7;
+    else if (n == "grid_sync_cycles") {  // tuning: average cycles of one grid barrier over 200 barriers
+      DevBuf c;
+      c.ensure(256 + 8);
+      CUDA_CHECK(cudaMemset(c.p, 0, 264));
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(tc::num_sms());
+      cfg.blockDim = dim3(tc::NUM_THREADS);
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeCooperative;
+      attr[0].val.cooperative = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      CUDA_CHECK(cudaLaunchKernelEx(&cfg, mega::grid_sync_bench_kernel, c.as<unsigned>(), 200,
+                                    reinterpret_cast<long long*>(static_cast<char*>(c.p) + 256)));
+      CUDA_CHECK(cudaDeviceSynchronize());
+      long long cyc = 0;
+      CUDA_CHECK(cudaMemcpy(&cyc, static_cast<char*>(c.p) + 256, 8, cudaMemcpyDeviceToHost));
+      c.release();
+      if (bytes < 8) throw std::runtime_error("need 8 bytes");
+      *static_cast<long long*>(host_dst) = cyc / 200;
+      return 0;
+    }
     else if (n == "mega_trace") {
       if (bytes > 256 * 8 || !e->mega_sync.p) throw std::runtime_error("no mega trace");
       CUDA_CHECK(cudaDeviceSynchronize());
-      CUDA_CHECK(cudaMemcpy(host_dst, static_cast<char*>(e->mega_sync.p) + 64, bytes, cudaMemcpyDeviceToHost));
+      CUDA_CHECK(cudaMemcpy(host_dst, static_cast<char*>(e->mega_sync.p) + 256, bytes, cudaMemcpyDeviceToHost));
       return 0;
     }
     else throw std::runtime_error("unknown debug buffer: " + n);

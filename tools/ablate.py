@@ -29,6 +29,8 @@ print("full step, dual halves   : %.3f ms" % run(0), flush=True)
 eng.set_option("dual", 0)
 base = run(0)
 print("full step                : %.3f ms" % base, flush=True)
+import numpy as np
+print("grid barrier: %d cycles" % int(eng.debug_read("grid_sync_cycles", (1,), np.int64)[0]), flush=True)
 eng.set_option("megakernel", 1 if "mega" in sys.argv else 0)
 print("full step, megakernel    : %.3f ms" % run(0), flush=True)
 import numpy as np
