@@ -905,7 +905,6 @@ struct rgrg_engine {
       ++launches;
     }
     pdl_now = opt_pdl != 0;
-    const int ln_grid = ceil_div(rows, 8);
     constexpr int SPLITS = 4;
     const size_t pstride = static_cast<size_t>(rows) * DM;
     float* parts = v.parts;
@@ -918,10 +917,10 @@ struct rgrg_engine {
         return;
       }
       if (pending_bias)
-        launch_kernel(dec::layernorm_kernel<SPLITS>, dim3(ln_grid), dim3(256), 0, st, pdl_now, v.h, g, b, v.x, rows, parts, pstride,
+        launch_kernel(dec::layernorm_kernel<SPLITS>, dim3(rows), dim3(128), 0, st, pdl_now, v.h, g, b, v.x, rows, parts, pstride,
                       pending_bias);
       else
-        launch_kernel(dec::layernorm_kernel<0>, dim3(ln_grid), dim3(256), 0, st, pdl_now, v.h, g, b, v.x, rows, parts, pstride,
+        launch_kernel(dec::layernorm_kernel<0>, dim3(rows), dim3(128), 0, st, pdl_now, v.h, g, b, v.x, rows, parts, pstride,
                       pending_bias);
       ++launches;
       pending_bias = nullptr;
@@ -1778,7 +1777,7 @@ int rgrg_gemm_bench(rgrg_engine_t* e, int M, int N, int K, int bn, int iters, in
         s.trace = (rep == 1 && i == iters - 1) ? T.as<long long>() : nullptr;
         e->launch_bn(bn, tmA, L, s, ep, st);
         if (interleave)
-          dec::layernorm_kernel<0><<<ceil_div(M, 8), 256, 0, st>>>(H.as<float>(), G.as<float>(), G.as<float>(), A.as<bf16>(), M, nullptr, 0,
+          dec::layernorm_kernel<0><<<M, 128, 0, st>>>(H.as<float>(), G.as<float>(), G.as<float>(), A.as<bf16>(), M, nullptr, 0,
                                                                   nullptr);
       }
       if (rep == 1) CUDA_CHECK(cudaEventRecord(b, st));
