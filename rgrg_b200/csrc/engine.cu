@@ -171,6 +171,7 @@ struct rgrg_engine {
   int opt_cuda_graph = 1;
   int opt_gemm_impl = 0;
   int opt_pdl = 1;
+  int opt_attn_bulk = 0;   // greedy attention through TMA bulk copies (decoder_kernels.cuh attention_bulk_kernel)
   int opt_dual = 0;        // greedy decode step as two concurrent row halves (two streams inside the step graph)
   int opt_megakernel = 0;  // greedy decode step as ONE persistent cooperative kernel (decoder_megakernel.cuh)
   int opt_ablate = 0;  // tuning only: bit mask of decode-step kernels to skip (results become meaningless, timing attributes cost)
@@ -930,7 +931,21 @@ struct rgrg_engine {
       ln(L.ln1_g, L.ln1_b);
       EpiQkvAppend eq{v.q, L.attn.bias, v.kv, l, sp};
       if (!(opt_ablate & 4)) gemm("c_attn", v.x, rows, L.attn, eq, st, true);
-      if (!(opt_ablate & 1)) {
+      // greedy path: TMA bulk-copy attention when a warp's double-buffered K / V blocks fit (2+ warps per CTA)
+      const size_t attn_per_warp = static_cast<size_t>(ws_slots) * 128 * 4;
+      const int attn_warps = static_cast<int>(std::min<size_t>(dec::ATTN_BULK_MAX_WARPS, (200 * 1024) / attn_per_warp));
+      if (!(opt_ablate & 1) && opt_attn_bulk && !beam_anc && attn_warps >= 2) {
+        ProfScope ps(this, "attention", st);
+        const size_t smem = attn_per_warp * attn_warps;
+        static size_t configured_smem = 0;
+        if (smem > configured_smem) {
+          CUDA_CHECK(cudaFuncSetAttribute(dec::attention_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+          configured_smem = smem;
+        }
+        const int grid = std::min(ceil_div(rows * 16, attn_warps), tc::num_sms());
+        launch_kernel(dec::attention_bulk_kernel, dim3(grid), dim3(attn_warps * 32), smem, st, pdl_now, v.q, v.kv, l, sp, v.attn_o, rows);
+        ++launches;
+      } else if (!(opt_ablate & 1)) {
         ProfScope ps(this, "attention", st);
         launch_kernel(dec::attention_kernel, dim3(ceil_div(rows * 16, 4)), dim3(128), 0, st, pdl_now, v.q, v.kv, l, sp, v.attn_o, rows,
                       beam_anc, beam_slots, beam_nb);
@@ -1453,6 +1468,12 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "pdl") e->opt_pdl = value;
   else if (k == "megakernel") e->opt_megakernel = value;
   else if (k == "dual") e->opt_dual = value;
+  else if (k == "attn_bulk") {
+    e->opt_attn_bulk = value;
+    for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.second);
+    e->step_graphs.clear();
+    e->step_graph_nodes.clear();
+  }
   else if (k == "ablate") {
     e->opt_ablate = value;
     for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.second);

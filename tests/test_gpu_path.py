@@ -170,3 +170,14 @@ def test_bbox_features_entry(model, synth_sd, images, golden):
     assert _rel(feats.cpu(), ref) < 0.05  # bf16 backbone
     ids = model.language_model.generate(feats, max_length=5)
     assert ids.shape == (58, 5)
+
+
+def test_bulk_copy_attention_matches_gather_attention(model, oracle_detail):
+    """The TMA bulk-copy attention kernel and the gather (LDG) attention kernel compute the same reduction order."""
+    eng = model._engine()
+    feats = torch.cat([oracle_detail["sel_feats"]] * 3, 0).contiguous().cuda()
+    eng.set_option("attn_bulk", 0)
+    a = eng.lm_generate(feats, 20)
+    eng.set_option("attn_bulk", 1)
+    b = eng.lm_generate(feats, 20)
+    assert np.array_equal(a, b)
