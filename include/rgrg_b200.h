@@ -143,7 +143,7 @@ RGRG_API int rgrg_backbone(rgrg_engine_t* e, const float* images_dev, int B, int
 RGRG_API int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst, size_t bytes);
 
 /* behaviour switches: "implicit_conv" (0/1), "cuda_graph" (0/1), "gemm_impl" (0 tcgen05, 2 CUDA-core cross-check),
- * "attn_bulk" (0/1: greedy attention through TMA bulk copies instead of gathered loads), "dual" (0/1: greedy decode step as two concurrent row halves), "megakernel" (0/1: greedy decode step as one persistent cooperative kernel), "pdl" (0/1: programmatic dependent launch between the kernels of a decode step), "profile" (0/1: record CUDA events around every kernel category on the launch stream; disables graph replay) */
+ * "ln_tail" (0/1: LayerNorm fused into the tail of the preceding split-K projection), "attn_bulk" (0/1: greedy attention through TMA bulk copies instead of gathered loads), "dual" (0/1: greedy decode step as two concurrent row halves), "megakernel" (0/1: greedy decode step as one persistent cooperative kernel), "pdl" (0/1: programmatic dependent launch between the kernels of a decode step), "profile" (0/1: record CUDA events around every kernel category on the launch stream; disables graph replay) */
 RGRG_API int rgrg_set_option(rgrg_engine_t* e, const char* key, int value);
 
 /* per-category device time since "profile" was switched on: text lines "<category> <total ms> <launches>\n" */

@@ -775,3 +775,13 @@ __global__ void beam_step_end_kernel(BeamState s, int sentences) {
 
 }  // namespace dec
 }  // namespace rgrg
+
+// definition of the LayerNorm tail hook declared in gemm_tc.cuh (split-K factor is always 4 on this path)
+namespace rgrg {
+namespace tc {
+__device__ void ln_row_tail(float* h, const float* gamma, const float* beta, bf16* out, int row, int lane, const float* parts,
+                            size_t part_stride, const float* res_bias, int nparts) {
+  dec::ln_row_dev<4>(h, gamma, beta, out, row, lane, parts, part_stride, res_bias);
+}
+}  // namespace tc
+}  // namespace rgrg

@@ -171,6 +171,7 @@ struct rgrg_engine {
   int opt_cuda_graph = 1;
   int opt_gemm_impl = 0;
   int opt_pdl = 1;
+  int opt_ln_tail = 0;     // LayerNorm (+ split-K reduce + residual) as the tail of the preceding projection GEMM
   int opt_attn_bulk = 0;   // greedy attention through TMA bulk copies (decoder_kernels.cuh attention_bulk_kernel)
   int opt_dual = 0;        // greedy decode step as two concurrent row halves (two streams inside the step graph)
   int opt_megakernel = 0;  // greedy decode step as ONE persistent cooperative kernel (decoder_megakernel.cuh)
@@ -197,7 +198,7 @@ struct rgrg_engine {
   DevBuf lm_in;
   // ---- workspace (decoder)
   int ws_rows = 0, ws_slots = 0;
-  DevBuf splitk_parts, mega_params, mega_sync;
+  DevBuf splitk_parts, mega_params, mega_sync, ln_counters;
   int mega_rows = -1, mega_ld = -1;
   DevBuf kv_cache, h, x, q, attn_o, mlp_mid, a1, img, part_val, part_idx, ids, unfinished, unf_count, step, logits_tmp;
   int last_B = 0, last_S = 0, last_P = 0;
@@ -222,7 +223,7 @@ struct rgrg_engine {
                      &prop_scores, &prop_count, &roi_off, &pooled, &f6, &f7, &pred_out, &detected, &top_idx,
                      &top_scores, &top_boxes, &mean2048, &trf, &s0, &s1, &sel_logits, &selected, &sel_rows, &num_sel,
                      &lm_in, &kv_cache, &h, &x, &q, &attn_o, &mlp_mid, &a1, &img, &part_val, &part_idx, &ids,
-                     &unfinished, &unf_count, &step, &logits_tmp, &splitk_parts, &mega_params, &mega_sync, &b_ids2, &b_anc[0], &b_anc[1], &b_scores, &b_cand_score,
+                     &unfinished, &unf_count, &step, &logits_tmp, &splitk_parts, &mega_params, &mega_sync, &ln_counters, &b_ids2, &b_anc[0], &b_anc[1], &b_scores, &b_cand_score,
                      &b_cand_token, &b_cand_beam, &b_hyp_score, &b_hyp_len, &b_hyp_tok, &b_hyp_count, &b_worst, &b_done, &b_not_done};
     for (DevBuf* b : all) b->release();
   }
@@ -274,7 +275,9 @@ struct rgrg_engine {
 
   // split-K GEMM for the two residual projections of a decoder layer (M = rows is only ~8 tiles tall): partial sums of
   // slice s go to parts[s] (fp32 [M, N]); the LayerNorm that follows adds them (+ bias) into the residual stream.
-  void gemm_splitk(const char* tag, const bf16* A, int M, const Linear& W, float* parts, int splits, cudaStream_t st) {
+  // ln != null: the GEMM's tail also performs the reduce + residual + LayerNorm that would otherwise be the next kernel
+  void gemm_splitk(const char* tag, const bf16* A, int M, const Linear& W, float* parts, int splits, cudaStream_t st,
+                   const tc::GemmShape::LnTail* ln = nullptr) {
     if (M <= 0) return;
     ProfScope ps(this, tag, st);
     auto ep = epi<false, ACT_NONE, RES_NONE, false>(parts, nullptr, W.N);
@@ -294,6 +297,11 @@ struct rgrg_engine {
     s.n_tiles = ceil_div(W.N, 256);
     s.m_fastest = 1;
     if (s.k_iters % splits) throw std::runtime_error("split-K factor must divide K / 64");
+    if (ln) {
+      if (s.m_tiles * s.n_tiles * splits > tc::num_sms() || tc::BM % (s.n_tiles * splits))
+        throw std::runtime_error("LayerNorm tail needs one co-resident tile per CTA");
+      s.ln = *ln;
+    }
     CUtensorMap tmA = tc::make_tmap_2d(A, M, W.K, 128);
     launch_bn(256, tmA, W, s, ep, st);
     ++launches;
@@ -843,6 +851,7 @@ struct rgrg_engine {
       attn_o.ensure(rr * DM * 2);
       mlp_mid.ensure(rr * 4 * DM * 2);
       splitk_parts.ensure(rr * DM * 4 * 4);
+      ln_counters.ensure(64 * 4);
       a1.ensure(rr * DM * 2);
       img.ensure(rr * DM * 2);
       part_val.ensure(rr * 2048 * 4);
@@ -878,10 +887,12 @@ struct rgrg_engine {
     KvGeom kv;
     float* part_val;
     int* part_idx;
+    int counter_base;  // first LayerNorm-tail counter of this view (one per M tile)
   };
   DecView dec_view(int row0, int rows) {
     DecView v;
     v.rows = rows;
+    v.counter_base = row0 ? 32 : 0;
     v.h = h.as<float>() + static_cast<size_t>(row0) * DM;
     v.x = x.as<bf16>() + static_cast<size_t>(row0) * DM;
     v.q = q.as<bf16>() + static_cast<size_t>(row0) * DM;
@@ -926,9 +937,10 @@ struct rgrg_engine {
       ++launches;
       pending_bias = nullptr;
     };
+    bool ln_done = false;  // the previous layer's mlp c_proj tail already produced this layer's ln_1 output
     for (int l = 0; l < NLAYER; ++l) {
       const LayerW& L = layers[l];
-      ln(L.ln1_g, L.ln1_b);
+      if (!ln_done) ln(L.ln1_g, L.ln1_b);
       EpiQkvAppend eq{v.q, L.attn.bias, v.kv, l, sp};
       if (!(opt_ablate & 4)) gemm("c_attn", v.x, rows, L.attn, eq, st, true);
       // greedy path: TMA bulk-copy attention when a warp's double-buffered K / V blocks fit (2+ warps per CTA)
@@ -951,15 +963,44 @@ struct rgrg_engine {
                       beam_anc, beam_slots, beam_nb);
         ++launches;
       }
-      if (!(opt_ablate & 8)) gemm_splitk("attn_c_proj", v.attn_o, rows, L.proj, parts, SPLITS, st);
-      pending_bias = L.proj.bias;
-      ln(L.ln2_g, L.ln2_b);
+      // (not with two concurrent halves: the tail's group barrier needs every CTA of the GEMM resident at once)
+      const bool fuse_ln = opt_ln_tail && !in_dual && opt_gemm_impl != 2 && !opt_ablate && ceil_div(rows, tc::BM) * 4 * SPLITS <= tc::num_sms();
+      tc::GemmShape::LnTail lt{};
+      lt.h = v.h;
+      lt.x = v.x;
+      lt.parts = parts;
+      lt.part_stride = pstride;
+      lt.counters = ln_counters.as<unsigned>() + v.counter_base;
+      lt.step_ptr = sp;
+      lt.launches_per_step = 2 * NLAYER;
+      if (fuse_ln) {
+        lt.gamma = L.ln2_g;
+        lt.beta = L.ln2_b;
+        lt.res_bias = L.proj.bias;
+        lt.launch_idx = 2 * l;
+        gemm_splitk("attn_c_proj", v.attn_o, rows, L.proj, parts, SPLITS, st, &lt);
+      } else {
+        if (!(opt_ablate & 8)) gemm_splitk("attn_c_proj", v.attn_o, rows, L.proj, parts, SPLITS, st);
+        pending_bias = L.proj.bias;
+        ln(L.ln2_g, L.ln2_b);
+      }
       if (!(opt_ablate & 16))
         gemm("mlp_c_fc", v.x, rows, L.fc, epi<true, ACT_GELU_NEW, RES_NONE, true>(v.mid, L.fc.bias, 4 * DM), st, true);
-      if (!(opt_ablate & 32)) gemm_splitk("mlp_c_proj", v.mid, rows, L.mproj, parts, SPLITS, st);
-      pending_bias = L.mproj.bias;
+      if (fuse_ln) {
+        // the tail of mlp c_proj is the NEXT LayerNorm: ln_1 of layer l+1, or the final LayerNorm
+        lt.gamma = (l + 1 < NLAYER) ? layers[l + 1].ln1_g : lnf_g;
+        lt.beta = (l + 1 < NLAYER) ? layers[l + 1].ln1_b : lnf_b;
+        lt.res_bias = L.mproj.bias;
+        lt.launch_idx = 2 * l + 1;
+        gemm_splitk("mlp_c_proj", v.mid, rows, L.mproj, parts, SPLITS, st, &lt);
+        ln_done = true;
+      } else {
+        if (!(opt_ablate & 32)) gemm_splitk("mlp_c_proj", v.mid, rows, L.mproj, parts, SPLITS, st);
+        pending_bias = L.mproj.bias;
+        ln_done = false;
+      }
     }
-    ln(lnf_g, lnf_b);
+    if (!ln_done) ln(lnf_g, lnf_b);
   }
   void end_pdl() { pdl_now = false; }
 
@@ -999,6 +1040,7 @@ struct rgrg_engine {
   // one greedy decode step as TWO independent row halves on two streams: decode rows never interact, and the kernels
   // of a half are latency-bound (profiles/r01_decode_ablation.md), so the halves overlap each other's launch / ramp /
   // drain bubbles and one half's HBM-bound attention runs beside the other half's tensor-core GEMMs.
+  bool in_dual = false;
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int decode_step_dual(int rows, const dec::GreedyState& g, cudaStream_t st) {
@@ -1013,6 +1055,7 @@ struct rgrg_engine {
     const int rows_b = rows - rows_a;
     CUDA_CHECK(cudaEventRecord(ev_fork, st));
     CUDA_CHECK(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+    in_dual = true;
     for (int b = 0; b < 2; ++b) {
       const int row0 = b ? rows_a : 0;
       cudaStream_t s = b ? side_stream : st;
@@ -1025,6 +1068,7 @@ struct rgrg_engine {
       decode_forward(v, gb.ids, gb.ids_ld, s);
       decode_head(v, gb, nullptr, s);
     }
+    in_dual = false;
     CUDA_CHECK(cudaEventRecord(ev_join, side_stream));
     CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
     dec::step_advance_kernel<<<1, 32, 0, st>>>(g.step_ptr);
@@ -1165,6 +1209,7 @@ struct rgrg_engine {
     logits_tmp.ensure(static_cast<size_t>(rows) * VOCAB * 4);
     dec::BeamState s = beam_state(R, nb, max_length, early);
     lm_prologue(feats_bf16, R, nb, st);
+    CUDA_CHECK(cudaMemsetAsync(ln_counters.p, 0, 64 * 4, st));
     dec::beam_init_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(s, R);
     KERNEL_CHECK();
     ++launches;
@@ -1295,6 +1340,7 @@ struct rgrg_engine {
     g.step_ptr = step.as<int>();
     g.ticket = step.as<int>() + 1;
     g.advance = 1;
+    CUDA_CHECK(cudaMemsetAsync(ln_counters.p, 0, 64 * 4, st));
     dec::greedy_init_kernel<<<ceil_div(std::max(R, max_length), 256), 256, 0, st>>>(g, R);
     KERNEL_CHECK();
     ++launches;
@@ -1468,6 +1514,12 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "pdl") e->opt_pdl = value;
   else if (k == "megakernel") e->opt_megakernel = value;
   else if (k == "dual") e->opt_dual = value;
+  else if (k == "ln_tail") {
+    e->opt_ln_tail = value;
+    for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.second);
+    e->step_graphs.clear();
+    e->step_graph_nodes.clear();
+  }
   else if (k == "attn_bulk") {
     e->opt_attn_bulk = value;
     for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.second);
@@ -1635,6 +1687,7 @@ int rgrg_lm_forced_logits(rgrg_engine_t* e, const float* feats_dev, int R, const
     g.ticket = e->step.as<int>() + 1;
     g.advance = 1;
     g.forced = forced_ids_dev;
+    CUDA_CHECK(cudaMemsetAsync(e->ln_counters.p, 0, 64 * 4, st));
     dec::greedy_init_kernel<<<ceil_div(std::max(R, n_tokens), 256), 256, 0, st>>>(g, R);
     KERNEL_CHECK();
     ++e->launches;

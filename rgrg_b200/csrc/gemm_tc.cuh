@@ -34,6 +34,20 @@ struct GemmShape {
   int tiles_w, tiles_h;  // output tiles per image: (W/16) x (H/8); one tile = 8 rows x 16 cols = 128 pixels
   long long* trace;      // optional [grid, 8] clock64 timeline of each CTA (bring-up / tuning only)
   int k_splits;          // split-K factor (0/1 = off): tile index -> (split, m, n); each split covers k_iters / k_splits blocks
+  // Optional tail of a split-K GEMM with one tile per CTA: once all n_tiles * k_splits CTAs of an M tile have stored their
+  // partial sums, each of them reduces + LayerNorms 128 / (n_tiles * k_splits) rows of that M tile (see the kernel).
+  struct LnTail {
+    float* h;             // fp32 residual stream [M, 1024]; null = no tail
+    const float* gamma;
+    const float* beta;
+    const float* res_bias;  // bias of this projection, added with the partial sums
+    bf16* x;              // normalised bf16 output [M, 1024]
+    const float* parts;   // this GEMM's own partial-sum slices
+    size_t part_stride;
+    unsigned* counters;   // [m_tiles] arrival counters, monotonic within a generate()
+    const int* step_ptr;  // device decode step: targets are derived from it so a captured graph can be replayed
+    int launch_idx, launches_per_step;
+  } ln;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -443,6 +457,44 @@ struct Pipe {
   }
 };
 
+// Reduce + LayerNorm tail of a split-K projection (one tile per CTA, all CTAs co-resident: grid <= #SMs).
+// The 16 CTAs that share an M tile meet at a per-M-tile counter; then CTA `rank` owns rows rank*8 .. rank*8+7 of the
+// tile, one row per epilogue warp: h += bias + sum of partial slices, x = LayerNorm(h).  This replaces a separate
+// LayerNorm kernel (one launch + one dependency bubble per projection) by a ~1.5 us group barrier.
+__device__ void ln_row_tail(float* h, const float* gamma, const float* beta, bf16* out, int row, int lane, const float* parts,
+                            size_t part_stride, const float* res_bias, int nparts);
+
+__device__ __forceinline__ void ln_tail(const GemmShape& s) {
+  __syncthreads();  // every epilogue warp of this CTA has issued its partial-sum stores
+  const TileCoord tc_ = tile_coord(s, blockIdx.x);
+  const int group = s.n_tiles * s.k_splits;
+  if (threadIdx.x == 0) {
+    const unsigned target =
+        static_cast<unsigned>(*s.ln.step_ptr * s.ln.launches_per_step + s.ln.launch_idx + 1) * static_cast<unsigned>(group);
+    unsigned* ctr = s.ln.counters + tc_.m_blk;
+    unsigned old;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr) : "memory");
+    long long start = clock64();
+    unsigned v = old + 1;
+    while (v < target) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (clock64() - start > 4000000000LL) {
+        printf("rgrg_b200: LayerNorm-tail group barrier timed out (block %d, count %u, target %u)\n", blockIdx.x, v, target);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = tc_.split * s.n_tiles + tc_.n_blk;
+  const int rows_per_cta = BM / group;
+  if (warp >= 2 && warp - 2 < rows_per_cta) {
+    const int row = tc_.m_blk * BM + rank * rows_per_cta + (warp - 2);
+    if (row < s.M)
+      ln_row_tail(s.ln.h, s.ln.gamma, s.ln.beta, s.ln.x, row, lane, s.ln.parts, s.ln.part_stride, s.ln.res_bias, s.k_splits);
+  }
+}
+
 template <int BN, int STAGES, class Epi>
 __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
@@ -477,6 +529,7 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
     pipe.epilogue(s, epi, it, trace);
   }
   if (trace && warp == 2 && lane == 0) trace[5] = clock64();
+  if (s.ln.h) ln_tail(s);
   pipe.teardown();
   if (trace && threadIdx.x == 0) trace[6] = clock64();
 }

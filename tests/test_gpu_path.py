@@ -181,3 +181,19 @@ def test_bulk_copy_attention_matches_gather_attention(model, oracle_detail):
     eng.set_option("attn_bulk", 1)
     b = eng.lm_generate(feats, 20)
     assert np.array_equal(a, b)
+
+
+def test_layernorm_tail_matches_separate_layernorm(model, oracle_detail):
+    """LayerNorm fused into the tail of the split-K projections vs separate LayerNorm kernels: same values up to the
+    reduction order inside a row (warp-per-row vs four warps per row)."""
+    eng = model._engine()
+    feats = torch.cat([oracle_detail["sel_feats"]] * 3, 0).contiguous().cuda()
+    eng.set_option("ln_tail", 0)
+    a = eng.lm_generate(feats, 16)
+    eng.set_option("ln_tail", 1)
+    b = eng.lm_generate(feats, 16)
+    eng.set_option("cuda_graph", 0)
+    c = eng.lm_generate(feats, 16)
+    eng.set_option("cuda_graph", 1)
+    assert np.array_equal(b, c)
+    assert np.array_equal(a[:, :4], b[:, :4]) and (a == b).mean() > 0.9
