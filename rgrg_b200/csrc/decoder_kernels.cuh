@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(128) layernorm_kernel(float* __restrict__ h, c
 // lane l holds dims (l%8)*8..+8 of key 4*i + l/8.
 // Beam search: `anc` (optional) maps (row, slot) to the beam of the same sentence whose physical cache row holds that
 // slot, so the reference's per-step index_select of the whole cache (language_model.py:492-496) becomes a table lookup.
+template <bool DOUBLE_BUFFER>
 __device__ __forceinline__ void attention_dev(const bf16* __restrict__ q, const KvGeom& kv, int layer, int L, bf16* __restrict__ out,
                                               int row, int head, int lane, const unsigned char* __restrict__ anc, int anc_ld, int nb) {
   const int sub = lane >> 3, dseg = lane & 7;
@@ -202,11 +203,13 @@ __device__ __forceinline__ void attention_dev(const bf16* __restrict__ q, const 
       vr[i] = __ldcg(reinterpret_cast<const uint4*>(vp + static_cast<size_t>(key) * HD + dseg * 8));
     }
   };
-  uint4 kcur[4], vcur[4], knext[4], vnext[4];
+  uint4 kcur[4], vcur[4], knext[DOUBLE_BUFFER ? 4 : 1], vnext[DOUBLE_BUFFER ? 4 : 1];
   load_chunk(0, kcur, vcur);
   for (int c0 = 0; c0 < L; c0 += 16) {
     const bool more = c0 + 16 < L;
-    if (more) load_chunk(c0 + 16, knext, vnext);
+    if constexpr (DOUBLE_BUFFER) {
+      if (more) load_chunk(c0 + 16, knext, vnext);
+    }
     float sc[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -237,12 +240,16 @@ __device__ __forceinline__ void attention_dev(const bf16* __restrict__ q, const 
       }
       m = m_new;
     }
-    if (more) {
+    if constexpr (DOUBLE_BUFFER) {
+      if (more) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        kcur[i] = knext[i];
-        vcur[i] = vnext[i];
+        for (int i = 0; i < 4; ++i) {
+          kcur[i] = knext[i];
+          vcur[i] = vnext[i];
+        }
       }
+    } else {
+      if (more) load_chunk(c0 + 16, kcur, vcur);
     }
   }
   // merge the 4 key subgroups (lanes differing in bits 3 and 4)
@@ -266,14 +273,17 @@ __device__ __forceinline__ void attention_dev(const bf16* __restrict__ q, const 
     *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * D + head * HD + dseg * 8) = pack8(acc);
   }
 }
-__global__ void __launch_bounds__(128) attention_kernel(const bf16* __restrict__ q, KvGeom kv, int layer,
-                                                        const int* __restrict__ step_ptr, bf16* __restrict__ out, int rows,
-                                                        const unsigned char* __restrict__ anc, int anc_ld, int nb) {
+// 6 CTAs (24 warps) per SM: a warp's lifetime is three dependent memory hops, so at small L the kernel is bound by how
+// many warps are resident, not by loads in flight per warp (single 16-key chunk buffer, <= 80 registers)
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(128, MIN_CTAS) attention_kernel(const bf16* __restrict__ q, KvGeom kv, int layer,
+                                                                  const int* __restrict__ step_ptr, bf16* __restrict__ out, int rows,
+                                                                  const unsigned char* __restrict__ anc, int anc_ld, int nb) {
   griddep_wait();
   griddep_launch_dependents();
   const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (gw >= rows * HEADS) return;
-  attention_dev(q, kv, layer, *step_ptr + 2, out, gw / HEADS, gw % HEADS, threadIdx.x & 31, anc, anc_ld, nb);
+  attention_dev<false>(q, kv, layer, *step_ptr + 2, out, gw / HEADS, gw % HEADS, threadIdx.x & 31, anc, anc_ld, nb);
 }
 
 // K18 (greedy path): the same attention with the K / V blocks of an item fetched by the TMA engine.

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 1) decoder_step_kernel(const 
     mark(trace, ti);
     // ---- attention over the cache
     for (int item = wg; item < rows * dec::HEADS; item += nw)
-      dec::attention_dev(P->q, P->kv, l, L, P->attn_o, item / dec::HEADS, item % dec::HEADS, lane, nullptr, 0, 1);
+      dec::attention_dev<true>(P->q, P->kv, l, L, P->attn_o, item / dec::HEADS, item % dec::HEADS, lane, nullptr, 0, 1);
     grid_sync(sync, gen);
     mark(trace, ti);
     // ---- attention c_proj, split-K partial sums

@@ -172,6 +172,7 @@ struct rgrg_engine {
   int opt_gemm_impl = 0;
   int opt_pdl = 1;
   int opt_ln_tail = 0;     // LayerNorm (+ split-K reduce + residual) as the tail of the preceding projection GEMM
+  int opt_attn_occ = 6;    // CTAs per SM the attention kernel is compiled for (6: 78 registers; 8: 64 registers, small spills)
   int opt_attn_bulk = 0;   // greedy attention through TMA bulk copies (decoder_kernels.cuh attention_bulk_kernel)
   int opt_dual = 0;        // greedy decode step as two concurrent row halves (two streams inside the step graph)
   int opt_megakernel = 0;  // greedy decode step as ONE persistent cooperative kernel (decoder_megakernel.cuh)
@@ -959,8 +960,12 @@ struct rgrg_engine {
         ++launches;
       } else if (!(opt_ablate & 1)) {
         ProfScope ps(this, "attention", st);
-        launch_kernel(dec::attention_kernel, dim3(ceil_div(rows * 16, 4)), dim3(128), 0, st, pdl_now, v.q, v.kv, l, sp, v.attn_o, rows,
-                      beam_anc, beam_slots, beam_nb);
+        if (opt_attn_occ == 8)
+          launch_kernel(dec::attention_kernel<8>, dim3(ceil_div(rows * 16, 4)), dim3(128), 0, st, pdl_now, v.q, v.kv, l, sp, v.attn_o,
+                        rows, beam_anc, beam_slots, beam_nb);
+        else
+          launch_kernel(dec::attention_kernel<6>, dim3(ceil_div(rows * 16, 4)), dim3(128), 0, st, pdl_now, v.q, v.kv, l, sp, v.attn_o,
+                        rows, beam_anc, beam_slots, beam_nb);
         ++launches;
       }
       // (not with two concurrent halves: the tail's group barrier needs every CTA of the GEMM resident at once)
@@ -1516,6 +1521,12 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "dual") e->opt_dual = value;
   else if (k == "ln_tail") {
     e->opt_ln_tail = value;
+    for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.second);
+    e->step_graphs.clear();
+    e->step_graph_nodes.clear();
+  }
+  else if (k == "attn_occ") {
+    e->opt_attn_occ = value;
     for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.second);
     e->step_graphs.clear();
     e->step_graph_nodes.clear();

@@ -24,6 +24,9 @@ def run(mask, pdl=1, graph=1):
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / n / (T - 1) * 1e3  # ms per decode step
 
+eng.set_option("attn_occ", 8)
+print("full step, attention 8 CTAs/SM: %.3f ms" % run(0), flush=True)
+eng.set_option("attn_occ", 6)
 eng.set_option("dual", 1)
 print("full step, dual halves   : %.3f ms" % run(0), flush=True)
 eng.set_option("dual", 0)
