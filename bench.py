@@ -104,7 +104,8 @@ class ClockSampler:
 
 
 def log(msg):
-    print("[bench %s] %s" % (time.strftime("%H:%M:%S"), msg), file=sys.stderr, flush=True)
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench %s] %s" % (time.strftime("%H:%M:%S"), msg), file=sys.stderr, flush=True)
 
 
 def timed_oracle_generate(sd, img, T, decode_budget_s=25.0):
