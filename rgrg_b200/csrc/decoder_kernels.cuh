@@ -273,8 +273,8 @@ __device__ __forceinline__ void attention_dev(const bf16* __restrict__ q, const 
     *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * D + head * HD + dseg * 8) = pack8(acc);
   }
 }
-// 6 CTAs (24 warps) per SM: a warp's lifetime is three dependent memory hops, so at small L the kernel is bound by how
-// many warps are resident, not by loads in flight per warp (single 16-key chunk buffer, <= 80 registers)
+// MIN_CTAS CTAs per SM (7 -> 28 warps, 72 registers, measured best of 5..8): a warp's lifetime is three dependent memory hops, so at small L the kernel is bound by how
+// many warps are resident, not by loads in flight per warp (single 16-key chunk buffer)
 template <int MIN_CTAS>
 __global__ void __launch_bounds__(128, MIN_CTAS) attention_kernel(const bf16* __restrict__ q, KvGeom kv, int layer,
                                                                   const int* __restrict__ step_ptr, bf16* __restrict__ out, int rows,

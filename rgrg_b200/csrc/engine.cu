@@ -172,7 +172,8 @@ struct rgrg_engine {
   int opt_gemm_impl = 0;
   int opt_pdl = 1;
   int opt_ln_tail = 0;     // LayerNorm (+ split-K reduce + residual) as the tail of the preceding projection GEMM
-  int opt_attn_occ = 6;    // CTAs per SM the attention kernel is compiled for (6: 78 registers; 8: 64 registers, small spills)
+  int opt_cattn_bn = 0;    // tuning: force the N tile of c_attn (0 = pick_bn)
+  int opt_attn_occ = 7;    // CTAs per SM the attention kernel is compiled for (5: 88 regs, 6: 78, 7: 72, 8: 64 + small spills)
   int opt_attn_bulk = 0;   // greedy attention through TMA bulk copies (decoder_kernels.cuh attention_bulk_kernel)
   int opt_dual = 0;        // greedy decode step as two concurrent row halves (two streams inside the step graph)
   int opt_megakernel = 0;  // greedy decode step as ONE persistent cooperative kernel (decoder_megakernel.cuh)
@@ -943,7 +944,7 @@ struct rgrg_engine {
       const LayerW& L = layers[l];
       if (!ln_done) ln(L.ln1_g, L.ln1_b);
       EpiQkvAppend eq{v.q, L.attn.bias, v.kv, l, sp};
-      if (!(opt_ablate & 4)) gemm("c_attn", v.x, rows, L.attn, eq, st, true);
+      if (!(opt_ablate & 4)) gemm("c_attn", v.x, rows, L.attn, eq, st, true, opt_cattn_bn);
       // greedy path: TMA bulk-copy attention when a warp's double-buffered K / V blocks fit (2+ warps per CTA)
       const size_t attn_per_warp = static_cast<size_t>(ws_slots) * 128 * 4;
       const int attn_warps = static_cast<int>(std::min<size_t>(dec::ATTN_BULK_MAX_WARPS, (200 * 1024) / attn_per_warp));
@@ -960,11 +961,17 @@ struct rgrg_engine {
         ++launches;
       } else if (!(opt_ablate & 1)) {
         ProfScope ps(this, "attention", st);
-        if (opt_attn_occ == 8)
+        if (opt_attn_occ == 6)
+          launch_kernel(dec::attention_kernel<6>, dim3(ceil_div(rows * 16, 4)), dim3(128), 0, st, pdl_now, v.q, v.kv, l, sp, v.attn_o,
+                        rows, beam_anc, beam_slots, beam_nb);
+        else if (opt_attn_occ == 5)
+          launch_kernel(dec::attention_kernel<5>, dim3(ceil_div(rows * 16, 4)), dim3(128), 0, st, pdl_now, v.q, v.kv, l, sp, v.attn_o,
+                        rows, beam_anc, beam_slots, beam_nb);
+        else if (opt_attn_occ == 8)
           launch_kernel(dec::attention_kernel<8>, dim3(ceil_div(rows * 16, 4)), dim3(128), 0, st, pdl_now, v.q, v.kv, l, sp, v.attn_o,
                         rows, beam_anc, beam_slots, beam_nb);
         else
-          launch_kernel(dec::attention_kernel<6>, dim3(ceil_div(rows * 16, 4)), dim3(128), 0, st, pdl_now, v.q, v.kv, l, sp, v.attn_o,
+          launch_kernel(dec::attention_kernel<7>, dim3(ceil_div(rows * 16, 4)), dim3(128), 0, st, pdl_now, v.q, v.kv, l, sp, v.attn_o,
                         rows, beam_anc, beam_slots, beam_nb);
         ++launches;
       }
@@ -1525,8 +1532,9 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
     e->step_graphs.clear();
     e->step_graph_nodes.clear();
   }
-  else if (k == "attn_occ") {
-    e->opt_attn_occ = value;
+  else if (k == "attn_occ" || k == "cattn_bn") {
+    if (k == "attn_occ") e->opt_attn_occ = value;
+    else e->opt_cattn_bn = value;
     for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.second);
     e->step_graphs.clear();
     e->step_graph_nodes.clear();

@@ -24,12 +24,16 @@ def run(mask, pdl=1, graph=1):
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / n / (T - 1) * 1e3  # ms per decode step
 
-eng.set_option("attn_occ", 8)
-print("full step, attention 8 CTAs/SM: %.3f ms" % run(0), flush=True)
-eng.set_option("attn_occ", 6)
-eng.set_option("dual", 1)
-print("full step, dual halves   : %.3f ms" % run(0), flush=True)
-eng.set_option("dual", 0)
+if "variants" in sys.argv:
+    for occ in (5, 7, 6):
+        eng.set_option("attn_occ", occ)
+        print("full step, attention %d CTAs/SM: %.3f ms" % (occ, run(0)), flush=True)
+    for bn in (256, 128, 0):
+        eng.set_option("cattn_bn", bn)
+        print("full step, c_attn N tile %s: %.3f ms" % (bn or "auto (192)", run(0)), flush=True)
+    eng.set_option("dual", 1)
+    print("full step, dual halves   : %.3f ms" % run(0), flush=True)
+    eng.set_option("dual", 0)
 base = run(0)
 print("full step                : %.3f ms" % base, flush=True)
 import numpy as np
