@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(ATTN_BULK_MAX_WARPS * 32) attention_bulk_kerne
   }
 }
 
-// K22/K23  arg-max over the vocabulary + greedy bookkeeping (language_model.py:629-650).  One CTA.
+// K22/K23  arg-max over the vocabulary + greedy bookkeeping (language_model.py:629-650).  One warp per row.
 //   next = argmax(logits) (lowest index on ties); finished rows emit pad; ids[:, t+1] = next; a row finishes when it
 //   emits EOS; unfinished_count[t] lets the host stop early without a per-step sync; the last CTA does step += 1.
 // Source of the arg-max: tile partials of the fused lm_head epilogue (part_*), or a full fp32 logits matrix.

@@ -1,7 +1,9 @@
+// EXPERIMENTAL (opt-in, `rgrg_set_option("megakernel", 1)`; token-checked against the default path).
 // One persistent kernel per decode step (greedy mode): the whole 24-layer transformer body, the lm_head with its fused
 // arg-max and the greedy bookkeeping run as PHASES of a single cooperative launch, separated by grid barriers
-// (~1.5 us) instead of kernel boundaries (~5 us each, 172 of them per step in the multi-kernel path, which is what
-// bounded the decode loop: see profiles/r01_decode_ablation.md).
+// (2.0 us each, measured) instead of kernel boundaries (172 per step in the default multi-kernel path).
+// Measured slower than the default (3.1 vs 2.4 ms / step): with ten warps per SM the row-parallel phases are
+// latency-bound and the GEMM phases keep their fill / drain cost; see profiles/r01_decode_experiments.md.
 //
 //   grid  = one CTA per SM (cooperative launch: all CTAs are co-resident, which the grid barrier requires)
 //   block = 320 threads: the tile pipeline of gemm_tc.cuh (warp 0 TMA, warp 1 MMA, warps 2..9 epilogue) during GEMM

@@ -1,8 +1,8 @@
 // tcgen05 + TMA GEMM for sm_100a:  D[M,N] = A[M,K] * W[N,K]^T   (bf16 operands, fp32 accumulate in TMEM)
 //
 // Persistent: one CTA per SM walks 128 x BN output tiles; two TMEM accumulator stages overlap the epilogue of one
-// tile with the main loop of the next.  Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA
-// issuer, warps 2..5 epilogue (see the kernel).
+// tile with the main loop of the next.  Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA
+// issuer, warps 2..9 epilogue (see tc::Pipe).
 //
 // Operand A is fetched either through a 2-D tensor map over a row-major [M,K] matrix (plain GEMM: every Linear /
 // Conv1D / 1x1 conv of the path) or through a 4-D tensor map over an NHWC activation (implicit-GEMM 3x3 conv,
