@@ -222,7 +222,7 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": "reports_per_sec", "value": value, "unit": "reports/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1, world),
+        "config": workload_config(args, args.batch, world),  # the SAME workload as the GPU arm; `sample` says what was timed
         "cpu_baseline": {"value": value, "unit": "reports/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "reports/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
