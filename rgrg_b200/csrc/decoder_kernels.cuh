@@ -37,8 +37,8 @@ __device__ __forceinline__ void embed_row_dev(const float* __restrict__ wte, int
 }
 __global__ void __launch_bounds__(256) embed_kernel(const float* __restrict__ wte, const int* __restrict__ ids, int ids_ld,
                                                     const int* __restrict__ step_ptr, float* __restrict__ h, int rows) {
+  griddep_launch_dependents();  // dependents may be scheduled now; they block at their own griddep_wait until this grid completes
   griddep_wait();
-  griddep_launch_dependents();
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (r >= rows) return;
   const int t = *step_ptr;
@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(128) layernorm_kernel(float* __restrict__ h, c
     *reinterpret_cast<float4*>(rb) = *reinterpret_cast<const float4*>(res_bias + c0);
     *reinterpret_cast<float4*>(rb + 4) = *reinterpret_cast<const float4*>(res_bias + c0 + 4);
   }
+  griddep_launch_dependents();  // dependents may be scheduled now; they block at their own griddep_wait until this grid completes
   griddep_wait();
-  griddep_launch_dependents();
   const int row = blockIdx.x;
   float* hp = h + static_cast<size_t>(row) * D + c0;
   float v[8];
@@ -279,8 +279,8 @@ template <int MIN_CTAS>
 __global__ void __launch_bounds__(128, MIN_CTAS) attention_kernel(const bf16* __restrict__ q, KvGeom kv, int layer,
                                                                   const int* __restrict__ step_ptr, bf16* __restrict__ out, int rows,
                                                                   const unsigned char* __restrict__ anc, int anc_ld, int nb) {
+  griddep_launch_dependents();  // dependents may be scheduled now; they block at their own griddep_wait until this grid completes
   griddep_wait();
-  griddep_launch_dependents();
   const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (gw >= rows * HEADS) return;
   attention_dev<false>(q, kv, layer, *step_ptr + 2, out, gw / HEADS, gw % HEADS, threadIdx.x & 31, anc, anc_ld, nb);
@@ -339,8 +339,8 @@ __global__ void __launch_bounds__(ATTN_BULK_MAX_WARPS * 32) attention_bulk_kerne
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
+  griddep_launch_dependents();  // dependents may be scheduled now; they block at their own griddep_wait until this grid completes
   griddep_wait();
-  griddep_launch_dependents();
   const int L = *step_ptr + 2;
   const uint32_t bytes = static_cast<uint32_t>(L) * 128;
   const int total = rows * HEADS;
