@@ -167,7 +167,8 @@ def nms_keep(boxes: torch.Tensor, thresh: float) -> torch.Tensor:
         w = np.maximum(np.float32(0), xx2 - xx1)
         h = np.maximum(np.float32(0), yy2 - yy1)
         inter = w * h
-        ovr = inter / (areas[i] + areas[i + 1:] - inter)
+        with np.errstate(invalid="ignore", divide="ignore"):  # 0/0 for two zero-area boxes is NaN and never suppresses, as in the C++ kernel
+            ovr = inter / (areas[i] + areas[i + 1:] - inter)
         suppressed[i + 1:] |= ovr > thr
     return torch.as_tensor(keep, dtype=torch.int64)
 
