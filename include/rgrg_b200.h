@@ -142,8 +142,20 @@ RGRG_API int rgrg_backbone(rgrg_engine_t* e, const float* images_dev, int B, int
  * "features" bf16 [B,f,f,2048], "pred_out" fp32 [P,150], "proposals" fp32 [B,1000,4], "selection_logits" fp32 [B*29] */
 RGRG_API int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst, size_t bytes);
 
-/* behaviour switches: "implicit_conv" (0/1), "cuda_graph" (0/1), "gemm_impl" (0 tcgen05, 2 CUDA-core cross-check),
- * "ln_tail" (0/1: LayerNorm fused into the tail of the preceding split-K projection), "attn_bulk" (0/1: greedy attention through TMA bulk copies instead of gathered loads), "dual" (0/1: greedy decode step as two concurrent row halves), "megakernel" (0/1: greedy decode step as one persistent cooperative kernel), "pdl" (0/1: programmatic dependent launch between the kernels of a decode step), "profile" (0/1: record CUDA events around every kernel category on the launch stream; disables graph replay) */
+/* behaviour switches (every change drops the cached decode-step graphs):
+ *   "cuda_graph" (0/1)        replay one captured graph per decode step
+ *   "pdl" (0/1)               programmatic dependent launch between the kernels of a decode step
+ *   "fused_attn" (0/1)        greedy decode: c_attn + KV append + attention as one head-aligned kernel (attn_fused.cuh);
+ *                             0 = c_attn GEMM (KV-append epilogue) + stand-alone attention kernel (always used by beam search)
+ *   "ln_head" (0/1)           LayerNorm (+ split-K reduce + residual) as the 16-CTA-cluster head of the consumer GEMM;
+ *                             0 = separate LayerNorm kernels
+ *   "attn_slots" (3/4/5)      fused attention: K/V ring slots per warp;  "l2_ahead" (n): items prefetched into L2
+ *   "attn_occ" (5..8), "cattn_bn" (0/128/192/256)   tuning of the two-kernel attention path
+ *   "implicit_conv" (0/1)     3x3 convs as TMA implicit GEMM (1) or im2col + GEMM (0)
+ *   "gemm_impl" (0/2)         0 tcgen05, 2 CUDA-core cross-check of every bf16 GEMM
+ *   "detector_precise" (0/1)  fp32 detector (parity mode: fp32 operands and activations on CUDA cores)
+ *   "ablate" (bit mask)       tuning only: skip kernel groups of the decode step to attribute time
+ *   "profile" (0/1)           record CUDA events around every kernel category on the launch stream (disables graph replay) */
 RGRG_API int rgrg_set_option(rgrg_engine_t* e, const char* key, int value);
 
 /* per-category device time since "profile" was switched on: text lines "<category> <total ms> <launches>\n" */

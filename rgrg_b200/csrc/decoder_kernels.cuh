@@ -286,167 +286,6 @@ __global__ void __launch_bounds__(128, MIN_CTAS) attention_kernel(const bf16* __
   attention_dev<false>(q, kv, layer, *step_ptr + 2, out, gw / HEADS, gw % HEADS, threadIdx.x & 31, anc, anc_ld, nb);
 }
 
-// K18 (greedy path): the same attention with the K / V blocks of an item fetched by the TMA engine.
-// ncu on attention_kernel shows warps parked on `long_scoreboard` with DRAM at ~50-60 %: the LSU's outstanding-load
-// capacity per SM, not HBM, bounds it.  Here every warp is persistent and double-buffered: one lane issues two 1-D bulk
-// copies (cp.async.bulk, complete_tx on an mbarrier) for the NEXT (row, head) item — L x 128 contiguous bytes of K
-// and of V — while the warp reduces the current item out of shared memory, so an SM keeps ~100 KB in flight
-// without occupying load/store-unit request slots.  (Beam search keeps the gather kernel: its rows are not contiguous.)
-__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr_u32(dst)),
-               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_addr_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  long long start = clock64();
-  while (!ok) {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(ok)
-        : "r"(smem_addr_u32(bar)), "r"(parity)
-        : "memory");
-    if (!ok && clock64() - start > 4000000000LL) {
-      printf("rgrg_b200: attention bulk-copy wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
-  }
-}
-
-constexpr int ATTN_BULK_MAX_WARPS = 6;
-
-// dynamic smem: per warp 2 buffers x (K block + V block), each block = slots_cap * 128 bytes
-__global__ void __launch_bounds__(ATTN_BULK_MAX_WARPS * 32) attention_bulk_kernel(const bf16* __restrict__ q, KvGeom kv, int layer,
-                                                                                  const int* __restrict__ step_ptr,
-                                                                                  bf16* __restrict__ out, int rows) {
-  extern __shared__ __align__(128) uint8_t attn_smem[];
-  __shared__ uint64_t s_bar[ATTN_BULK_MAX_WARPS][2];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwb = blockDim.x >> 5;
-  const int sub = lane >> 3, dseg = lane & 7;
-  const size_t blk_bytes = static_cast<size_t>(kv.slots_cap) * 128;
-  uint8_t* my = attn_smem + static_cast<size_t>(warp) * 4 * blk_bytes;  // [buf][K|V][slots_cap * 128]
-  if (lane == 0) {
-    bar_init(&s_bar[warp][0], 1);
-    bar_init(&s_bar[warp][1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncwarp();
-  griddep_launch_dependents();  // dependents may be scheduled now; they block at their own griddep_wait until this grid completes
-  griddep_wait();
-  const int L = *step_ptr + 2;
-  const uint32_t bytes = static_cast<uint32_t>(L) * 128;
-  const int total = rows * HEADS;
-  const int wg = blockIdx.x * nwb + warp;
-  const int nw = gridDim.x * nwb;
-  if (wg >= total) return;
-
-  auto issue = [&](int item, int buf) {
-    if (lane == 0) {
-      const int row = item / HEADS, head = item % HEADS;
-      bar_expect_tx(&s_bar[warp][buf], 2 * bytes);
-      bulk_g2s(my + (buf * 2 + 0) * blk_bytes, kv.cache + kv.offset(layer, 0, row, head, 0), bytes, &s_bar[warp][buf]);
-      bulk_g2s(my + (buf * 2 + 1) * blk_bytes, kv.cache + kv.offset(layer, 1, row, head, 0), bytes, &s_bar[warp][buf]);
-    }
-  };
-  auto load_q = [&](int item) {
-    return __ldcg(reinterpret_cast<const uint4*>(q + static_cast<size_t>(item / HEADS) * D + (item % HEADS) * HD + dseg * 8));
-  };
-
-  int item = wg, buf = 0;
-  uint32_t phase[2] = {0, 0};
-  issue(item, 0);
-  uint4 qraw = load_q(item);
-  while (true) {
-    const int nxt = item + nw;
-    uint4 qnext = qraw;
-    if (nxt < total) {
-      __syncwarp();  // every lane is done reading buffer buf^1 (previous item) before it is refilled
-      issue(nxt, buf ^ 1);
-      qnext = load_q(nxt);
-    }
-    float qv[8];
-    unpack8(qraw, qv);
-    bar_wait(&s_bar[warp][buf], phase[buf]);
-    phase[buf] ^= 1;
-    const uint8_t* Kb = my + (buf * 2 + 0) * blk_bytes;
-    const uint8_t* Vb = my + (buf * 2 + 1) * blk_bytes;
-    float m = -INFINITY, den = 0.0f;
-    float acc[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
-    for (int c0 = 0; c0 < L; c0 += 16) {
-      float sc[4];
-      uint4 vr[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        int key = c0 + i * 4 + sub;
-        const bool ok = key < L;
-        key = ok ? key : L - 1;
-        float kf[8];
-        unpack8(*reinterpret_cast<const uint4*>(Kb + static_cast<size_t>(key) * 128 + dseg * 16), kf);
-        vr[i] = *reinterpret_cast<const uint4*>(Vb + static_cast<size_t>(key) * 128 + dseg * 16);
-        float part = 0.0f;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) part = fmaf(qv[e], kf[e], part);
-        part += __shfl_xor_sync(0xffffffffu, part, 1);
-        part += __shfl_xor_sync(0xffffffffu, part, 2);
-        part += __shfl_xor_sync(0xffffffffu, part, 4);
-        sc[i] = ok ? part * 0.125f : -INFINITY;  // / sqrt(64)   (language_model.py:88)
-      }
-      const float m_new = fmaxf(fmaxf(m, fmaxf(sc[0], sc[1])), fmaxf(sc[2], sc[3]));
-      if (m_new > -INFINITY) {
-        const float corr = __expf(m - m_new);
-        den *= corr;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] *= corr;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float p = __expf(sc[i] - m_new);
-          den += p;
-          float vf[8];
-          unpack8(vr[i], vf);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vf[e], acc[e]);
-        }
-        m = m_new;
-      }
-    }
-    // merge the 4 key subgroups (lanes differing in bits 3 and 4), normalise, store
-    float M = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
-    M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 16));
-    const float sc_merge = (m == -INFINITY) ? 0.0f : __expf(m - M);
-    den *= sc_merge;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] *= sc_merge;
-    den += __shfl_xor_sync(0xffffffffu, den, 8);
-    den += __shfl_xor_sync(0xffffffffu, den, 16);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
-      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
-    }
-    if (sub == 0) {
-      const float inv = 1.0f / den;
-      float o[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = acc[e] * inv;
-      *reinterpret_cast<uint4*>(out + static_cast<size_t>(item / HEADS) * D + (item % HEADS) * HD + dseg * 8) = pack8(o);
-    }
-    if (nxt >= total) break;
-    item = nxt;
-    buf ^= 1;
-    qraw = qnext;
-  }
-}
-
 // K22/K23  arg-max over the vocabulary + greedy bookkeeping (language_model.py:629-650).  One warp per row.
 //   next = argmax(logits) (lowest index on ties); finished rows emit pad; ids[:, t+1] = next; a row finishes when it
 //   emits EOS; unfinished_count[t] lets the host stop early without a per-step sync; the last CTA does step += 1.
@@ -457,7 +296,7 @@ struct GreedyState {
   int* unfinished;   // [rows] 1 = still generating
   int* unfinished_count;  // [max_steps], zeroed by greedy_init_kernel
   int* ticket;       // CTA arrival counter of greedy_update_kernel
-  int advance;       // 1: the last CTA of greedy_update_kernel publishes step + 1 (0 when two halves run concurrently)
+  int live_rows;     // rows >= live_rows are padding (row count rounded up for graph reuse): born finished, never counted
   int* step_ptr;
   const int* forced; // optional [rows, ids_ld]: teacher forcing — ids[:, t+1] = forced[:, t+1], arg-max is only recorded
   int* argmax_out;   // optional [max_steps, rows] raw arg-max per step (tests)
@@ -518,27 +357,19 @@ __global__ void __launch_bounds__(256) greedy_update_kernel(const float* __restr
     const int ticket = atomicAdd(g.ticket, 1);
     if (ticket == static_cast<int>(gridDim.x) - 1) {
       *g.ticket = 0;
-      if (g.advance) *g.step_ptr = t + 1;
+      *g.step_ptr = t + 1;
     }
   }
-}
-
-__global__ void step_advance_kernel(int* step_ptr) {
-  if (threadIdx.x == 0) *step_ptr += 1;
 }
 
 // start of a generate() call: ids[:, 0] = BOS, unfinished = 1, step = 0
 __global__ void greedy_init_kernel(GreedyState g, int rows) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < g.ids_ld) g.unfinished_count[r] = 0;
-  if (r == 0) {
-    g.ticket[0] = 0;
-    g.ticket[1] = 0;
-    g.ticket[2] = 0;
-  }
+  if (r == 0) g.ticket[0] = 0;
   if (r < rows) {
     g.ids[static_cast<size_t>(r) * g.ids_ld] = g.forced ? g.forced[static_cast<size_t>(r) * g.ids_ld] : EOS_ID;
-    g.unfinished[r] = 1;
+    g.unfinished[r] = r < g.live_rows ? 1 : 0;
   }
   if (r == 0) *g.step_ptr = 0;
 }
@@ -786,12 +617,13 @@ __global__ void beam_step_end_kernel(BeamState s, int sentences) {
 }  // namespace dec
 }  // namespace rgrg
 
-// definition of the LayerNorm tail hook declared in gemm_tc.cuh (split-K factor is always 4 on this path)
+// definition of the LayerNorm-head hook declared in gemm_tc.cuh (split-K factor is always 4 on this path)
 namespace rgrg {
 namespace tc {
-__device__ void ln_row_tail(float* h, const float* gamma, const float* beta, bf16* out, int row, int lane, const float* parts,
-                            size_t part_stride, const float* res_bias, int nparts) {
-  dec::ln_row_dev<4>(h, gamma, beta, out, row, lane, parts, part_stride, res_bias);
+__device__ __forceinline__ void ln_head_row(float* h, const float* gamma, const float* beta, bf16* x, int row, int lane,
+                                            const float* parts, size_t part_stride, const float* res_bias) {
+  if (parts) dec::ln_row_dev<4>(h, gamma, beta, x, row, lane, parts, part_stride, res_bias);
+  else dec::ln_row_dev<0>(h, gamma, beta, x, row, lane, nullptr, 0, nullptr);
 }
 }  // namespace tc
 }  // namespace rgrg

@@ -624,11 +624,17 @@ __global__ void __launch_bounds__(1024) selection_tail_kernel(const float* __res
   if (threadIdx.x == 0) *num_selected = run;
 }
 
-// gather the selected rows' fp32 features as the bf16 A operand of the decoder's first GEMM
+// gather the selected rows' fp32 features as the bf16 A operand of the decoder's first GEMM; rows [n, round_up(n, 32))
+// are zero-filled (the decoder runs on a padded row count so that its step graph is reused across batches)
 __global__ void gather_rows_bf16_kernel(const float* __restrict__ src, const int* __restrict__ rows, const int* __restrict__ n_rows,
                                         bf16* __restrict__ dst, int D) {
   const int r = blockIdx.x;
-  if (r >= *n_rows) return;
+  const int n = *n_rows;
+  if (r >= ((n + 31) & ~31)) return;
+  if (r >= n) {
+    for (int i = threadIdx.x; i < D; i += blockDim.x) dst[static_cast<size_t>(r) * D + i] = f2bf(0.0f);
+    return;
+  }
   const float* s = src + static_cast<size_t>(rows[r]) * D;
   for (int i = threadIdx.x; i < D; i += blockDim.x) dst[static_cast<size_t>(r) * D + i] = f2bf(s[i]);
 }

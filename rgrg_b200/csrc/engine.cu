@@ -16,8 +16,8 @@
 
 #include "../../include/rgrg_b200.h"
 #include "common.cuh"
+#include "attn_fused.cuh"
 #include "decoder_kernels.cuh"
-#include "decoder_megakernel.cuh"
 #include "detector_kernels.cuh"
 #include "epilogues.cuh"
 #include "gemm_simt.cuh"
@@ -36,10 +36,13 @@ constexpr int TOPK = det::TOPK;
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  // grow-only; the new block is allocated BEFORE the old one is freed, so a failed growth leaves the buffer usable
   void ensure(size_t n) {
     if (n <= bytes) return;
-    release();
-    CUDA_CHECK(cudaMalloc(&p, n));
+    void* np = nullptr;
+    CUDA_CHECK(cudaMalloc(&np, n));
+    if (p) cudaFree(p);
+    p = np;
     bytes = n;
   }
   void release() {
@@ -171,12 +174,13 @@ struct rgrg_engine {
   int opt_cuda_graph = 1;
   int opt_gemm_impl = 0;
   int opt_pdl = 1;
-  int opt_ln_tail = 0;     // LayerNorm (+ split-K reduce + residual) as the tail of the preceding projection GEMM
-  int opt_cattn_bn = 0;    // tuning: force the N tile of c_attn (0 = pick_bn)
-  int opt_attn_occ = 7;    // CTAs per SM the attention kernel is compiled for (5: 88 regs, 6: 78, 7: 72, 8: 64 + small spills)
-  int opt_attn_bulk = 0;   // greedy attention through TMA bulk copies (decoder_kernels.cuh attention_bulk_kernel)
-  int opt_dual = 0;        // greedy decode step as two concurrent row halves (two streams inside the step graph)
-  int opt_megakernel = 0;  // greedy decode step as ONE persistent cooperative kernel (decoder_megakernel.cuh)
+  int opt_detector_precise = 0;  // fp32 detector (parity mode, see run_detect)
+  int opt_fused_attn = 1;  // greedy decode: c_attn + KV append + attention as ONE head-aligned kernel (attn_fused.cuh)
+  int opt_ln_head = 1;     // LayerNorm (+ split-K reduce + residual) as the cluster-cooperative head of the consumer GEMM
+  int opt_attn_slots = 4;  // fused attention: shared-memory K/V ring slots per warp (3, 4 or 5)
+  int opt_l2_ahead = 2;    // fused attention: items whose K/V blocks are prefetched into L2 ahead of the consumer
+  int opt_cattn_bn = 0;    // tuning: force the N tile of c_attn (0 = pick_bn); two-kernel attention path only
+  int opt_attn_occ = 7;    // CTAs per SM the stand-alone attention kernel is compiled for (5: 88 regs, 6: 78, 7: 72, 8: 64)
   int opt_ablate = 0;  // tuning only: bit mask of decode-step kernels to skip (results become meaningless, timing attributes cost)
   bool pdl_now = false;  // set while the decode step is being issued: its kernels carry the PDL launch attribute
   std::unordered_map<std::string, HostRef> host;
@@ -200,8 +204,7 @@ struct rgrg_engine {
   DevBuf lm_in;
   // ---- workspace (decoder)
   int ws_rows = 0, ws_slots = 0;
-  DevBuf splitk_parts, mega_params, mega_sync, ln_counters;
-  int mega_rows = -1, mega_ld = -1;
+  DevBuf splitk_parts;
   DevBuf kv_cache, h, x, q, attn_o, mlp_mid, a1, img, part_val, part_idx, ids, unfinished, unf_count, step, logits_tmp;
   int last_B = 0, last_S = 0, last_P = 0;
   // beam search: cache-slot ancestry of the current step (null in greedy mode)
@@ -216,16 +219,13 @@ struct rgrg_engine {
     for (auto& g : step_graphs) cudaGraphExecDestroy(g.second);
     for (cudaEvent_t ev : prof_pool) cudaEventDestroy(ev);
     if (ev_enter) cudaEventDestroy(ev_enter);
-    if (ev_fork) cudaEventDestroy(ev_fork);
-    if (ev_join) cudaEventDestroy(ev_join);
-    if (side_stream) cudaStreamDestroy(side_stream);
     if (own_stream) cudaStreamDestroy(own_stream);
     for (void* p : weight_allocs) cudaFree(p);
     DevBuf* all[] = {&images, &act[0], &act[1], &t1, &t2, &idb, &sub, &col, &feats, &rpn_t, &rpn_out, &prop_boxes,
                      &prop_scores, &prop_count, &roi_off, &pooled, &f6, &f7, &pred_out, &detected, &top_idx,
                      &top_scores, &top_boxes, &mean2048, &trf, &s0, &s1, &sel_logits, &selected, &sel_rows, &num_sel,
                      &lm_in, &kv_cache, &h, &x, &q, &attn_o, &mlp_mid, &a1, &img, &part_val, &part_idx, &ids,
-                     &unfinished, &unf_count, &step, &logits_tmp, &splitk_parts, &mega_params, &mega_sync, &ln_counters, &b_ids2, &b_anc[0], &b_anc[1], &b_scores, &b_cand_score,
+                     &unfinished, &unf_count, &step, &logits_tmp, &splitk_parts, &b_ids2, &b_anc[0], &b_anc[1], &b_scores, &b_cand_score,
                      &b_cand_token, &b_cand_beam, &b_hyp_score, &b_hyp_len, &b_hyp_tok, &b_hyp_count, &b_worst, &b_done, &b_not_done};
     for (DevBuf* b : all) b->release();
   }
@@ -277,9 +277,7 @@ struct rgrg_engine {
 
   // split-K GEMM for the two residual projections of a decoder layer (M = rows is only ~8 tiles tall): partial sums of
   // slice s go to parts[s] (fp32 [M, N]); the LayerNorm that follows adds them (+ bias) into the residual stream.
-  // ln != null: the GEMM's tail also performs the reduce + residual + LayerNorm that would otherwise be the next kernel
-  void gemm_splitk(const char* tag, const bf16* A, int M, const Linear& W, float* parts, int splits, cudaStream_t st,
-                   const tc::GemmShape::LnTail* ln = nullptr) {
+  void gemm_splitk(const char* tag, const bf16* A, int M, const Linear& W, float* parts, int splits, cudaStream_t st) {
     if (M <= 0) return;
     ProfScope ps(this, tag, st);
     auto ep = epi<false, ACT_NONE, RES_NONE, false>(parts, nullptr, W.N);
@@ -299,13 +297,28 @@ struct rgrg_engine {
     s.n_tiles = ceil_div(W.N, 256);
     s.m_fastest = 1;
     if (s.k_iters % splits) throw std::runtime_error("split-K factor must divide K / 64");
-    if (ln) {
-      if (s.m_tiles * s.n_tiles * splits > tc::num_sms() || tc::BM % (s.n_tiles * splits))
-        throw std::runtime_error("LayerNorm tail needs one co-resident tile per CTA");
-      s.ln = *ln;
-    }
     CUtensorMap tmA = tc::make_tmap_2d(A, M, W.K, 128);
     launch_bn(256, tmA, W, s, ep, st);
+    ++launches;
+  }
+
+  // GEMM with a LayerNorm head (decoder c_fc): N must be 16 tiles of 256; launched as clusters of 16 CTAs
+  template <class Epi>
+  void gemm_ln_head(const char* tag, const bf16* A, int M, const Linear& W, const Epi& epi, const tc::GemmShape::LnHead& lnh,
+                    cudaStream_t st) {
+    if (M <= 0) return;
+    ProfScope ps(this, tag, st);
+    if (W.N != 16 * 256 || W.K % 64) throw std::runtime_error("LayerNorm-head GEMM needs N = 4096");
+    tc::GemmShape s{};
+    s.M = M;
+    s.N = W.N;
+    s.k_iters = W.K / 64;
+    s.m_tiles = ceil_div(M, tc::BM);
+    s.n_tiles = 16;
+    s.m_fastest = 0;  // tile -> (m_blk = tile / 16, n_blk = tile % 16): a cluster is one M tile
+    s.lnh = lnh;
+    CUtensorMap tmA = tc::make_tmap_2d(A, M, W.K, 128);
+    tc::launch<256, 4, Epi, true>(tmA, W.tm[3], s, epi, st, pdl_now);
     ++launches;
   }
 
@@ -706,7 +719,7 @@ struct rgrg_engine {
     selected.ensure(rows);
     sel_rows.ensure(rows * 4);
     num_sel.ensure(4);
-    lm_in.ensure(rows * 1024 * 2);
+    lm_in.ensure((rows + 32) * 1024 * 2);
     ws_B = B;
     ws_S = S;
   }
@@ -827,7 +840,7 @@ struct rgrg_engine {
     det::selection_tail_kernel<<<1, 1024, 0, st>>>(s1.as<float>(), sel4.w, sel4.bias, detected.as<uint8_t>(), sel_logits.as<float>(),
                                                    selected.as<uint8_t>(), sel_rows.as<int>(), num_sel.as<int>(), rows);
     KERNEL_CHECK();
-    det::gather_rows_bf16_kernel<<<rows, 256, 0, st>>>(trf.as<float>(), sel_rows.as<int>(), num_sel.as<int>(), lm_in.as<bf16>(), 1024);
+    det::gather_rows_bf16_kernel<<<rows + 31, 256, 0, st>>>(trf.as<float>(), sel_rows.as<int>(), num_sel.as<int>(), lm_in.as<bf16>(), 1024);
     KERNEL_CHECK();
     launches += 5;
     int R = 0;
@@ -841,11 +854,21 @@ struct rgrg_engine {
   // ================================================================================================================
   // decoder
   // ================================================================================================================
+  void drop_step_graphs() {
+    for (auto& g : step_graphs) cudaGraphExecDestroy(g.second);
+    step_graphs.clear();
+    step_graph_nodes.clear();
+  }
+  // Growth is transactional: capacities are published only after every allocation succeeded; on failure the
+  // whole decoder workspace is released and the capacities reset, so the caller's next (smaller) batch starts clean —
+  // the reference's callers catch "out of memory" and carry on (evaluate_language_model.py:1207-1222).
   void ensure_decoder_ws(int rows, int max_length) {
     const int slots = max_length + 1;
-    if (rows > ws_rows || slots > ws_slots) {
-      const int r = std::max(rows, ws_rows), s = std::max(slots, ws_slots);
-      kv_cache.ensure(static_cast<size_t>(NLAYER) * 2 * r * 16 * s * 64 * 2);
+    if (rows <= ws_rows && slots <= ws_slots) return;
+    const int r = std::max(rows, ws_rows), sl = std::max(slots, ws_slots);
+    drop_step_graphs();  // buffers move: captured pointers would be stale
+    try {
+      kv_cache.ensure(static_cast<size_t>(NLAYER) * 2 * r * 16 * sl * 64 * 2);
       const size_t rr = static_cast<size_t>(r);
       h.ensure(rr * DM * 4);
       x.ensure(rr * DM * 2);
@@ -853,22 +876,23 @@ struct rgrg_engine {
       attn_o.ensure(rr * DM * 2);
       mlp_mid.ensure(rr * 4 * DM * 2);
       splitk_parts.ensure(rr * DM * 4 * 4);
-      ln_counters.ensure(64 * 4);
       a1.ensure(rr * DM * 2);
       img.ensure(rr * DM * 2);
       part_val.ensure(rr * 2048 * 4);
       part_idx.ensure(rr * 2048 * 4);
-      ids.ensure(rr * (s + 1) * 4);
+      ids.ensure(rr * (sl + 1) * 4);
       unfinished.ensure(rr * 4);
-      unf_count.ensure(static_cast<size_t>(s + 1) * 4);
+      unf_count.ensure(static_cast<size_t>(sl + 1) * 4);
       step.ensure(16);
-      ws_rows = r;
-      ws_slots = s;
-      mega_rows = -1;
-      for (auto& g : step_graphs) cudaGraphExecDestroy(g.second);  // buffers moved: captured pointers are stale
-      step_graphs.clear();
-      step_graph_nodes.clear();
+    } catch (...) {
+      DevBuf* all[] = {&kv_cache, &h, &x, &q, &attn_o, &mlp_mid, &splitk_parts, &a1, &img, &part_val, &part_idx, &ids,
+                       &unfinished, &unf_count, &step, &logits_tmp};
+      for (DevBuf* b : all) b->release();
+      ws_rows = ws_slots = 0;
+      throw;
     }
+    ws_rows = r;
+    ws_slots = sl;
   }
   KvGeom kv_geom() const { return KvGeom{kv_cache.as<bf16>(), ws_rows, ws_slots}; }
 
@@ -880,48 +904,65 @@ struct rgrg_engine {
     gemm("lm_image_kv", img.as<bf16>(), R, ukv, e, st, true);
   }
 
-  // a contiguous row range of the decoder workspace (the whole batch, or one of the two concurrent halves)
-  struct DecView {
-    int rows;
-    float* h;
-    bf16 *x, *q, *attn_o, *mid;
-    float* parts;
-    KvGeom kv;
-    float* part_val;
-    int* part_idx;
-    int counter_base;  // first LayerNorm-tail counter of this view (one per M tile)
-  };
-  DecView dec_view(int row0, int rows) {
-    DecView v;
-    v.rows = rows;
-    v.counter_base = row0 ? 32 : 0;
-    v.h = h.as<float>() + static_cast<size_t>(row0) * DM;
-    v.x = x.as<bf16>() + static_cast<size_t>(row0) * DM;
-    v.q = q.as<bf16>() + static_cast<size_t>(row0) * DM;
-    v.attn_o = attn_o.as<bf16>() + static_cast<size_t>(row0) * DM;
-    v.mid = mlp_mid.as<bf16>() + static_cast<size_t>(row0) * 4 * DM;
-    v.parts = splitk_parts.as<float>() + static_cast<size_t>(row0) * DM * 4;
-    v.kv = kv_geom();
-    v.kv.cache += static_cast<size_t>(row0) * 16 * ws_slots * 64;  // KvGeom::offset is linear in the row index
-    v.part_val = part_val.as<float>() + static_cast<size_t>(row0) * 2048;
-    v.part_idx = part_idx.as<int>() + static_cast<size_t>(row0) * 2048;
-    return v;
+  // is the 16-CTA cluster shape of the LayerNorm-head kernels launchable on this device?  (queried once)
+  int cluster16_ok = -1;
+  bool ln_head_available() {
+    if (cluster16_ok < 0) {
+      auto kern = fa::attn_fused_kernel<4, true>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::Smem<4>::TOTAL);
+      cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(16);
+      cfg.blockDim = dim3(tc::NUM_THREADS);
+      cfg.dynamicSmemBytes = fa::Smem<4>::TOTAL;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 16;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int n = 0;
+      const cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+      cudaGetLastError();
+      cluster16_ok = (e == cudaSuccess && n >= 1) ? n : 0;
+    }
+    return cluster16_ok > 0;
   }
 
-  // transformer body of one decode step for the rows of `v` (embedding .. final LayerNorm); every kernel reads the step
-  // index from device memory.  Leaves ln_f(h) as bf16 in v.x.  ids_ptr points at the first row of the view.
-  void decode_forward(const DecView& v, const int* ids_ptr, int ids_ld, cudaStream_t st) {
-    const int rows = v.rows;
+  template <bool LN_HEAD>
+  void launch_attn_fused(const CUtensorMap& tmA, const CUtensorMap& tmW, const fa::Params& fp, cudaStream_t st) {
+    switch (opt_attn_slots) {
+      case 3: fa::launch<3, LN_HEAD>(tmA, tmW, fp, st, pdl_now); break;
+      case 5: fa::launch<5, LN_HEAD>(tmA, tmW, fp, st, pdl_now); break;
+      default: fa::launch<4, LN_HEAD>(tmA, tmW, fp, st, pdl_now); break;
+    }
+  }
+
+  // Transformer body of one decode step for `rows` rows (embedding .. final LayerNorm); every kernel reads the step index
+  // from device memory, so a captured CUDA graph of the step is replayed for every t.  Leaves ln_f(h) as bf16 in x.
+  //
+  // Greedy path, per layer (4 kernels): [LN1 head + c_attn + KV append + attention] -> attn c_proj (split-K) ->
+  // [LN2 head + c_fc + gelu_new] -> mlp c_proj (split-K).  The two bracketed kernels run as clusters of 16 CTAs (one M
+  // tile) whose LayerNorm head also folds the preceding projection's partial sums + bias into the residual stream.
+  // Beam search (cache rows are gathered through the ancestry table) and the cross-check GEMM keep the 7-kernel form:
+  // LN1, c_attn (KV-append epilogue), attention, c_proj, LN2, c_fc, c_proj.
+  void decode_forward(int rows, const int* ids_ptr, int ids_ld, cudaStream_t st) {
     const int* sp = step.as<int>();
     {
       ProfScope ps(this, "embed", st);
-      launch_kernel(dec::embed_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, st, false, wte_f32, ids_ptr, ids_ld, sp, v.h, rows);
+      launch_kernel(dec::embed_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, st, false, wte_f32, ids_ptr, ids_ld, sp, h.as<float>(), rows);
       ++launches;
     }
     pdl_now = opt_pdl != 0;
     constexpr int SPLITS = 4;
     const size_t pstride = static_cast<size_t>(rows) * DM;
-    float* parts = v.parts;
+    float* parts = splitk_parts.as<float>();
+    float* hp = h.as<float>();
+    bf16* xp = x.as<bf16>();
+    const bool tensor_path = opt_gemm_impl != 2;
+    const bool use_fused = opt_fused_attn && !beam_anc && tensor_path;
+    const bool use_head = opt_ln_head && tensor_path && ln_head_available();
     // LayerNorm fused with the residual update of the preceding split-K projection (pending_bias != null)
     const float* pending_bias = nullptr;
     auto ln = [&](const float* g, const float* b) {
@@ -931,161 +972,110 @@ struct rgrg_engine {
         return;
       }
       if (pending_bias)
-        launch_kernel(dec::layernorm_kernel<SPLITS>, dim3(rows), dim3(128), 0, st, pdl_now, v.h, g, b, v.x, rows, parts, pstride,
-                      pending_bias);
+        launch_kernel(dec::layernorm_kernel<SPLITS>, dim3(rows), dim3(128), 0, st, pdl_now, hp, g, b, xp, rows, parts, pstride, pending_bias);
       else
-        launch_kernel(dec::layernorm_kernel<0>, dim3(rows), dim3(128), 0, st, pdl_now, v.h, g, b, v.x, rows, parts, pstride,
-                      pending_bias);
+        launch_kernel(dec::layernorm_kernel<0>, dim3(rows), dim3(128), 0, st, pdl_now, hp, g, b, xp, rows, parts, pstride, pending_bias);
       ++launches;
       pending_bias = nullptr;
     };
-    bool ln_done = false;  // the previous layer's mlp c_proj tail already produced this layer's ln_1 output
+    CUtensorMap tm_x{};
+    if (use_fused) tm_x = tc::make_tmap_2d(xp, rows, DM, 128);
     for (int l = 0; l < NLAYER; ++l) {
       const LayerW& L = layers[l];
-      if (!ln_done) ln(L.ln1_g, L.ln1_b);
-      EpiQkvAppend eq{v.q, L.attn.bias, v.kv, l, sp};
-      if (!(opt_ablate & 4)) gemm("c_attn", v.x, rows, L.attn, eq, st, true, opt_cattn_bn);
-      // greedy path: TMA bulk-copy attention when a warp's double-buffered K / V blocks fit (2+ warps per CTA)
-      const size_t attn_per_warp = static_cast<size_t>(ws_slots) * 128 * 4;
-      const int attn_warps = static_cast<int>(std::min<size_t>(dec::ATTN_BULK_MAX_WARPS, (200 * 1024) / attn_per_warp));
-      if (!(opt_ablate & 1) && opt_attn_bulk && !beam_anc && attn_warps >= 2) {
-        ProfScope ps(this, "attention", st);
-        const size_t smem = attn_per_warp * attn_warps;
-        static size_t configured_smem = 0;
-        if (smem > configured_smem) {
-          CUDA_CHECK(cudaFuncSetAttribute(dec::attention_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-          configured_smem = smem;
+      // ---- LN1 + c_attn + attention
+      if (use_fused) {
+        fa::Params fp{};
+        fp.bias = L.attn.bias;
+        fp.kv = kv_geom();
+        fp.layer = l;
+        fp.step_ptr = sp;
+        fp.attn_o = attn_o.as<bf16>();
+        fp.M = rows;
+        fp.l2_ahead = opt_l2_ahead;
+        if (use_head) {
+          fp.h = hp;
+          fp.x = xp;
+          fp.gamma = L.ln1_g;
+          fp.beta = L.ln1_b;
+          fp.parts = pending_bias ? parts : nullptr;
+          fp.part_stride = pstride;
+          fp.res_bias = pending_bias;
+          pending_bias = nullptr;
+        } else {
+          ln(L.ln1_g, L.ln1_b);
         }
-        const int grid = std::min(ceil_div(rows * 16, attn_warps), tc::num_sms());
-        launch_kernel(dec::attention_bulk_kernel, dim3(grid), dim3(attn_warps * 32), smem, st, pdl_now, v.q, v.kv, l, sp, v.attn_o, rows);
-        ++launches;
-      } else if (!(opt_ablate & 1)) {
-        ProfScope ps(this, "attention", st);
-        if (opt_attn_occ == 6)
-          launch_kernel(dec::attention_kernel<6>, dim3(ceil_div(rows * 16, 4)), dim3(128), 0, st, pdl_now, v.q, v.kv, l, sp, v.attn_o,
-                        rows, beam_anc, beam_slots, beam_nb);
-        else if (opt_attn_occ == 5)
-          launch_kernel(dec::attention_kernel<5>, dim3(ceil_div(rows * 16, 4)), dim3(128), 0, st, pdl_now, v.q, v.kv, l, sp, v.attn_o,
-                        rows, beam_anc, beam_slots, beam_nb);
-        else if (opt_attn_occ == 8)
-          launch_kernel(dec::attention_kernel<8>, dim3(ceil_div(rows * 16, 4)), dim3(128), 0, st, pdl_now, v.q, v.kv, l, sp, v.attn_o,
-                        rows, beam_anc, beam_slots, beam_nb);
-        else
-          launch_kernel(dec::attention_kernel<7>, dim3(ceil_div(rows * 16, 4)), dim3(128), 0, st, pdl_now, v.q, v.kv, l, sp, v.attn_o,
-                        rows, beam_anc, beam_slots, beam_nb);
-        ++launches;
-      }
-      // (not with two concurrent halves: the tail's group barrier needs every CTA of the GEMM resident at once)
-      const bool fuse_ln = opt_ln_tail && !in_dual && opt_gemm_impl != 2 && !opt_ablate && ceil_div(rows, tc::BM) * 4 * SPLITS <= tc::num_sms();
-      tc::GemmShape::LnTail lt{};
-      lt.h = v.h;
-      lt.x = v.x;
-      lt.parts = parts;
-      lt.part_stride = pstride;
-      lt.counters = ln_counters.as<unsigned>() + v.counter_base;
-      lt.step_ptr = sp;
-      lt.launches_per_step = 2 * NLAYER;
-      if (fuse_ln) {
-        lt.gamma = L.ln2_g;
-        lt.beta = L.ln2_b;
-        lt.res_bias = L.proj.bias;
-        lt.launch_idx = 2 * l;
-        gemm_splitk("attn_c_proj", v.attn_o, rows, L.proj, parts, SPLITS, st, &lt);
+        if (!(opt_ablate & 64)) {
+          ProfScope ps(this, "attn_fused", st);
+          if (use_head) launch_attn_fused<true>(tm_x, L.attn.tm[0], fp, st);
+          else launch_attn_fused<false>(tm_x, L.attn.tm[0], fp, st);
+          ++launches;
+        }
       } else {
-        if (!(opt_ablate & 8)) gemm_splitk("attn_c_proj", v.attn_o, rows, L.proj, parts, SPLITS, st);
-        pending_bias = L.proj.bias;
+        ln(L.ln1_g, L.ln1_b);
+        EpiQkvAppend eq{q.as<bf16>(), L.attn.bias, kv_geom(), l, sp};
+        if (!(opt_ablate & 4)) gemm("c_attn", xp, rows, L.attn, eq, st, true, opt_cattn_bn);
+        if (!(opt_ablate & 1)) {
+          ProfScope ps(this, "attention", st);
+          const dim3 grid(ceil_div(rows * 16, 4));
+          auto go = [&](auto kern) {
+            launch_kernel(kern, grid, dim3(128), 0, st, pdl_now, q.as<bf16>(), kv_geom(), l, sp, attn_o.as<bf16>(), rows, beam_anc,
+                          beam_slots, beam_nb);
+          };
+          if (opt_attn_occ == 6) go(dec::attention_kernel<6>);
+          else if (opt_attn_occ == 5) go(dec::attention_kernel<5>);
+          else if (opt_attn_occ == 8) go(dec::attention_kernel<8>);
+          else go(dec::attention_kernel<7>);
+          ++launches;
+        }
+      }
+      // ---- attention c_proj: split-K partial sums, reduced (+ bias, + residual) by the LayerNorm that follows
+      if (!(opt_ablate & 8)) gemm_splitk("attn_c_proj", attn_o.as<bf16>(), rows, L.proj, parts, SPLITS, st);
+      pending_bias = L.proj.bias;
+      // ---- LN2 + c_fc + gelu_new
+      auto ep_fc = epi<true, ACT_GELU_NEW, RES_NONE, true>(mlp_mid.p, L.fc.bias, 4 * DM);
+      if (use_head) {
+        tc::GemmShape::LnHead lh{hp, xp, L.ln2_g, L.ln2_b, parts, pstride, pending_bias};
+        pending_bias = nullptr;
+        if (!(opt_ablate & 16)) gemm_ln_head("mlp_c_fc", xp, rows, L.fc, ep_fc, lh, st);
+      } else {
         ln(L.ln2_g, L.ln2_b);
+        if (!(opt_ablate & 16)) gemm("mlp_c_fc", xp, rows, L.fc, ep_fc, st, true);
       }
-      if (!(opt_ablate & 16))
-        gemm("mlp_c_fc", v.x, rows, L.fc, epi<true, ACT_GELU_NEW, RES_NONE, true>(v.mid, L.fc.bias, 4 * DM), st, true);
-      if (fuse_ln) {
-        // the tail of mlp c_proj is the NEXT LayerNorm: ln_1 of layer l+1, or the final LayerNorm
-        lt.gamma = (l + 1 < NLAYER) ? layers[l + 1].ln1_g : lnf_g;
-        lt.beta = (l + 1 < NLAYER) ? layers[l + 1].ln1_b : lnf_b;
-        lt.res_bias = L.mproj.bias;
-        lt.launch_idx = 2 * l + 1;
-        gemm_splitk("mlp_c_proj", v.mid, rows, L.mproj, parts, SPLITS, st, &lt);
-        ln_done = true;
-      } else {
-        if (!(opt_ablate & 32)) gemm_splitk("mlp_c_proj", v.mid, rows, L.mproj, parts, SPLITS, st);
-        pending_bias = L.mproj.bias;
-        ln_done = false;
-      }
+      // ---- mlp c_proj
+      if (!(opt_ablate & 32)) gemm_splitk("mlp_c_proj", mlp_mid.as<bf16>(), rows, L.mproj, parts, SPLITS, st);
+      pending_bias = L.mproj.bias;
     }
-    if (!ln_done) ln(lnf_g, lnf_b);
+    ln(lnf_g, lnf_b);
   }
   void end_pdl() { pdl_now = false; }
 
-  // lm_head + greedy bookkeeping for one view.  logits_out != null: lm_head stores fp32 logits there instead of the
-  // fused arg-max.  `g` must already point at the view's first row.
-  void decode_head(const DecView& v, const dec::GreedyState& g, float* logits_out, cudaStream_t st) {
-    const int rows = v.rows;
+  // lm_head + greedy bookkeeping.  logits_out != null: lm_head stores fp32 logits there instead of the fused arg-max.
+  void decode_head(int rows, const dec::GreedyState& g, float* logits_out, cudaStream_t st) {
     if (logits_out || opt_gemm_impl == 2) {
       float* dst = logits_out ? logits_out : logits_tmp.as<float>();
-      gemm("lm_head", v.x, rows, lm_head, epi<false, ACT_NONE, RES_NONE, false>(dst, nullptr, VOCAB), st, true);
+      gemm("lm_head", x.as<bf16>(), rows, lm_head, epi<false, ACT_NONE, RES_NONE, false>(dst, nullptr, VOCAB), st, true);
       ProfScope ps(this, "greedy_update", st);
       launch_kernel(dec::greedy_update_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, st, pdl_now, static_cast<const float*>(nullptr),
                     static_cast<const int*>(nullptr), 0, static_cast<const float*>(dst), g, rows);
     } else {
       const int bn = pick_bn(ceil_div(rows, tc::BM), VOCAB);
       const int n_tiles = 2 * ceil_div(VOCAB, bn);  // two partials per tile: one per epilogue warp of a lane quarter
-      EpiArgmaxPartial ea{v.part_val, v.part_idx, n_tiles};
-      gemm("lm_head", v.x, rows, lm_head, ea, st, true, bn);
+      EpiArgmaxPartial ea{part_val.as<float>(), part_idx.as<int>(), n_tiles};
+      gemm("lm_head", x.as<bf16>(), rows, lm_head, ea, st, true, bn);
       ProfScope ps(this, "greedy_update", st);
       launch_kernel(dec::greedy_update_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, st, pdl_now,
-                    static_cast<const float*>(v.part_val), static_cast<const int*>(v.part_idx), n_tiles,
+                    static_cast<const float*>(part_val.as<float>()), static_cast<const int*>(part_idx.as<int>()), n_tiles,
                     static_cast<const float*>(nullptr), g, rows);
     }
     end_pdl();
     ++launches;
   }
 
-  // one greedy decode step over all rows, single chain
+  // one greedy decode step over all rows
   int decode_step(int rows, const dec::GreedyState& g, float* logits_out, cudaStream_t st) {
     const int before = static_cast<int>(launches);
-    DecView v = dec_view(0, rows);
-    decode_forward(v, g.ids, g.ids_ld, st);
-    decode_head(v, g, logits_out, st);
-    return static_cast<int>(launches) - before;
-  }
-
-  // one greedy decode step as TWO independent row halves on two streams: decode rows never interact, and the kernels
-  // of a half are latency-bound (profiles/r01_decode_ablation.md), so the halves overlap each other's launch / ramp /
-  // drain bubbles and one half's HBM-bound attention runs beside the other half's tensor-core GEMMs.
-  bool in_dual = false;
-  cudaStream_t side_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int decode_step_dual(int rows, const dec::GreedyState& g, cudaStream_t st) {
-    const int before = static_cast<int>(launches);
-    if (!side_stream) {
-      CUDA_CHECK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
-      CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-      CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-    }
-    int rows_a = ((rows / 2 + 127) / 128) * 128;  // split on an M-tile boundary: no extra tile padding
-    if (rows_a >= rows) rows_a = rows / 2;
-    const int rows_b = rows - rows_a;
-    CUDA_CHECK(cudaEventRecord(ev_fork, st));
-    CUDA_CHECK(cudaStreamWaitEvent(side_stream, ev_fork, 0));
-    in_dual = true;
-    for (int b = 0; b < 2; ++b) {
-      const int row0 = b ? rows_a : 0;
-      cudaStream_t s = b ? side_stream : st;
-      DecView v = dec_view(row0, b ? rows_b : rows_a);
-      dec::GreedyState gb = g;
-      gb.ids = g.ids + static_cast<size_t>(row0) * g.ids_ld;
-      gb.unfinished = g.unfinished + row0;
-      gb.ticket = g.ticket + 1 + b;
-      gb.advance = 0;
-      decode_forward(v, gb.ids, gb.ids_ld, s);
-      decode_head(v, gb, nullptr, s);
-    }
-    in_dual = false;
-    CUDA_CHECK(cudaEventRecord(ev_join, side_stream));
-    CUDA_CHECK(cudaStreamWaitEvent(st, ev_join, 0));
-    dec::step_advance_kernel<<<1, 32, 0, st>>>(g.step_ptr);
-    KERNEL_CHECK();
-    ++launches;
+    decode_forward(rows, g.ids, g.ids_ld, st);
+    decode_head(rows, g, logits_out, st);
     return static_cast<int>(launches) - before;
   }
 
@@ -1221,7 +1211,6 @@ struct rgrg_engine {
     logits_tmp.ensure(static_cast<size_t>(rows) * VOCAB * 4);
     dec::BeamState s = beam_state(R, nb, max_length, early);
     lm_prologue(feats_bf16, R, nb, st);
-    CUDA_CHECK(cudaMemsetAsync(ln_counters.p, 0, 64 * 4, st));
     dec::beam_init_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(s, R);
     KERNEL_CHECK();
     ++launches;
@@ -1231,8 +1220,7 @@ struct rgrg_engine {
     beam_nb = nb;
     for (int t = 0; t < steps; ++t) {
       beam_anc = s.anc[cur];
-      DecView v = dec_view(0, rows);
-      decode_forward(v, s.ids[cur], max_length, st);
+      decode_forward(rows, s.ids[cur], max_length, st);
       gemm("lm_head", x.as<bf16>(), rows, lm_head, epi<false, ACT_NONE, RES_NONE, false>(logits_tmp.p, nullptr, VOCAB), st, true);
       end_pdl();
       beam_bookkeeping(s, logits_tmp.as<float>(), R, cur, st);
@@ -1260,90 +1248,16 @@ struct rgrg_engine {
     return beam_finalize(s, R, cur_len, cur, max_length, out_ids, st);
   }
 
-  // ---- the decode step as one persistent cooperative kernel
-  void mega_prepare(int rows, const dec::GreedyState& g) {
-    if (mega_rows == rows && mega_ld == g.ids_ld) return;
-    mega::Params* hp = new mega::Params();
-    memset(hp, 0, sizeof(mega::Params));
-    for (int l = 0; l < NLAYER; ++l) {
-      const LayerW& L = layers[l];
-      mega::Layer& d = hp->layer[l];
-      d.tm_attn = L.attn.tm[3];
-      d.tm_proj = L.proj.tm[3];
-      d.tm_fc = L.fc.tm[3];
-      d.tm_mproj = L.mproj.tm[3];
-      d.ln1_g = L.ln1_g; d.ln1_b = L.ln1_b; d.ln2_g = L.ln2_g; d.ln2_b = L.ln2_b;
-      d.b_attn = L.attn.bias; d.b_proj = L.proj.bias; d.b_fc = L.fc.bias; d.b_mproj = L.mproj.bias;
-    }
-    hp->tm_x = tc::make_tmap_2d(x.p, rows, DM, 128);
-    hp->tm_attn_o = tc::make_tmap_2d(attn_o.p, rows, DM, 128);
-    hp->tm_mid = tc::make_tmap_2d(mlp_mid.p, rows, 4 * DM, 128);
-    hp->tm_lm_head = lm_head.tm[3];
-    auto shape = [&](int N, int K, int splits) {
-      tc::GemmShape s{};
-      s.M = rows;
-      s.N = N;
-      s.k_iters = K / 64;
-      s.k_splits = splits;
-      s.m_tiles = ceil_div(rows, tc::BM);
-      s.n_tiles = ceil_div(N, mega::BN);
-      s.m_fastest = 1;
-      return s;
-    };
-    hp->s_attn = shape(3 * DM, DM, 0);
-    hp->s_proj = shape(DM, DM, mega::SPLITS);
-    hp->s_fc = shape(4 * DM, DM, 0);
-    hp->s_mproj = shape(DM, 4 * DM, mega::SPLITS);
-    hp->s_head = shape(VOCAB, DM, 0);
-    hp->lnf_g = lnf_g; hp->lnf_b = lnf_b; hp->wte = wte_f32;
-    hp->h = h.as<float>(); hp->x = x.as<bf16>(); hp->q = q.as<bf16>(); hp->attn_o = attn_o.as<bf16>(); hp->mid = mlp_mid.as<bf16>();
-    hp->parts = splitk_parts.as<float>();
-    hp->kv = kv_geom();
-    hp->g = g;
-    hp->part_val = part_val.as<float>();
-    hp->part_idx = part_idx.as<int>();
-    hp->n_parts = 2 * ceil_div(VOCAB, mega::BN);
-    hp->rows = rows;
-    mega_sync.ensure(256 + 256 * 8);
-    hp->sync_counter = mega_sync.as<unsigned>();
-    hp->trace = reinterpret_cast<long long*>(static_cast<char*>(mega_sync.p) + 256);
-    mega_params.ensure(sizeof(mega::Params));
-    cudaError_t err = cudaMemcpy(mega_params.p, hp, sizeof(mega::Params), cudaMemcpyHostToDevice);
-    delete hp;
-    CUDA_CHECK(err);
-    static bool configured = false;
-    if (!configured) {
-      CUDA_CHECK(cudaFuncSetAttribute(mega::decoder_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      tc::SmemLayout<mega::BN, mega::STAGES>::TOTAL));
-      configured = true;
-    }
-    mega_rows = rows;
-    mega_ld = g.ids_ld;
-  }
-  int decode_step_mega(int rows, cudaStream_t st) {
-    ProfScope ps(this, "decoder_step_megakernel", st);
-    CUDA_CHECK(cudaMemsetAsync(mega_sync.p, 0, 256, st));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(tc::num_sms());
-    cfg.blockDim = dim3(tc::NUM_THREADS);
-    cfg.dynamicSmemBytes = tc::SmemLayout<mega::BN, mega::STAGES>::TOTAL;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    const mega::Params* dp = static_cast<const mega::Params*>(mega_params.p);
-    CUDA_CHECK(cudaLaunchKernelEx(&cfg, mega::decoder_step_kernel, dp));
-    launches += 1;
-    return 1;
-  }
-
-  // greedy decode of `R` rows whose features sit in feats_bf16; host ids [R, max_length], returns reference width
+  // Greedy decode of R rows whose bf16 features sit in feats_bf16 (zero-padded to round_up(R, 32) rows); host ids
+  // [R, max_length]; returns the reference width.  The step graph is keyed by the PADDED row count, so batches whose
+  // number of selected regions differs by a few rows replay the same graph (rows never interact; padded rows start
+  // "finished", emit EOS and are not counted).
+  static int padded_rows(int R) { return (R + 31) & ~31; }
   int run_greedy(const bf16* feats_bf16, int R, int max_length, int32_t* out_ids, cudaStream_t st) {
-    ensure_decoder_ws(R, max_length);
-    if (opt_gemm_impl == 2) logits_tmp.ensure(static_cast<size_t>(R) * VOCAB * 4);
-    lm_prologue(feats_bf16, R, 1, st);
+    const int Rp = padded_rows(R);
+    ensure_decoder_ws(Rp, max_length);
+    if (opt_gemm_impl == 2) logits_tmp.ensure(static_cast<size_t>(Rp) * VOCAB * 4);
+    lm_prologue(feats_bf16, Rp, 1, st);
     dec::GreedyState g{};
     g.ids = ids.as<int>();
     g.ids_ld = max_length;
@@ -1351,32 +1265,24 @@ struct rgrg_engine {
     g.unfinished_count = unf_count.as<int>();
     g.step_ptr = step.as<int>();
     g.ticket = step.as<int>() + 1;
-    g.advance = 1;
-    CUDA_CHECK(cudaMemsetAsync(ln_counters.p, 0, 64 * 4, st));
-    dec::greedy_init_kernel<<<ceil_div(std::max(R, max_length), 256), 256, 0, st>>>(g, R);
+    g.live_rows = R;
+    dec::greedy_init_kernel<<<ceil_div(std::max(Rp, max_length), 256), 256, 0, st>>>(g, Rp);
     KERNEL_CHECK();
     ++launches;
     const int steps = max_length - 1;
     cudaGraphExec_t exec = nullptr;
     int nodes = 0;
-    const int graph_key = (R * 4096 + max_length) * 2 + (opt_dual ? 1 : 0);
-    const bool use_mega = opt_megakernel && opt_gemm_impl != 2 && !opt_ablate;
-    if (use_mega) {
-      mega_prepare(R, g);
-      decode_step_mega(R, st);
-    } else {
-      // step 0 always runs eagerly (it also makes sure every kernel is loaded and configured before a capture)
-      decode_step(R, g, nullptr, st);
-    }
-    const bool use_dual = opt_dual && !use_mega && opt_gemm_impl != 2 && R >= 256;
-    if (!use_mega && opt_cuda_graph && !prof_on && steps > 1) {
+    const int graph_key = Rp * 4096 + max_length;
+    // step 0 always runs eagerly (it also makes sure every kernel is loaded and configured before a capture)
+    decode_step(Rp, g, nullptr, st);
+    if (opt_cuda_graph && !prof_on && steps > 1) {
       auto it = step_graphs.find(graph_key);
       if (it == step_graphs.end()) {
         cudaGraph_t graph;
         const int64_t saved = launches;
         CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         try {
-          nodes = use_dual ? decode_step_dual(R, g, st) : decode_step(R, g, nullptr, st);
+          nodes = decode_step(Rp, g, nullptr, st);
         } catch (...) {
           cudaGraph_t dead;
           cudaStreamEndCapture(st, &dead);
@@ -1393,18 +1299,14 @@ struct rgrg_engine {
         nodes = step_graph_nodes[graph_key];
       }
     }
-    int done_steps = 1;
+    int done_steps = steps > 0 ? 1 : 0;
     std::vector<int> counts(steps > 0 ? steps : 1);
     for (int t = 1; t < steps; ++t) {
-      if (use_mega) {
-        decode_step_mega(R, st);
-      } else if (exec) {
+      if (exec) {
         CUDA_CHECK(cudaGraphLaunch(exec, st));
         launches += nodes;
-      } else if (use_dual) {
-        decode_step_dual(R, g, st);
       } else {
-        decode_step(R, g, nullptr, st);
+        decode_step(Rp, g, nullptr, st);
       }
       ++done_steps;
       if ((t & 7) == 7 && t + 1 < steps) {  // early exit without a per-step sync (language_model.py:649)
@@ -1483,8 +1385,6 @@ int rgrg_create(int device, rgrg_engine_t** out) {
     e->device = device;
     const char* ic = getenv("RGRG_IMPLICIT_CONV");
     if (ic) e->opt_implicit_conv = atoi(ic);
-    const char* mk = getenv("RGRG_MEGAKERNEL");
-    if (mk) e->opt_megakernel = atoi(mk);
     *out = e;
     return 0;
   } catch (const std::exception& ex) {
@@ -1524,37 +1424,19 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "cuda_graph") e->opt_cuda_graph = value;
   else if (k == "gemm_impl") e->opt_gemm_impl = value;
   else if (k == "pdl") e->opt_pdl = value;
-  else if (k == "megakernel") e->opt_megakernel = value;
-  else if (k == "dual") e->opt_dual = value;
-  else if (k == "ln_tail") {
-    e->opt_ln_tail = value;
-    for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.second);
-    e->step_graphs.clear();
-    e->step_graph_nodes.clear();
-  }
-  else if (k == "attn_occ" || k == "cattn_bn") {
-    if (k == "attn_occ") e->opt_attn_occ = value;
-    else e->opt_cattn_bn = value;
-    for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.second);
-    e->step_graphs.clear();
-    e->step_graph_nodes.clear();
-  }
-  else if (k == "attn_bulk") {
-    e->opt_attn_bulk = value;
-    for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.second);
-    e->step_graphs.clear();
-    e->step_graph_nodes.clear();
-  }
-  else if (k == "ablate") {
-    e->opt_ablate = value;
-    for (auto& g : e->step_graphs) cudaGraphExecDestroy(g.second);
-    e->step_graphs.clear();
-    e->step_graph_nodes.clear();
-  }
+  else if (k == "fused_attn") e->opt_fused_attn = value;
+  else if (k == "ln_head") e->opt_ln_head = value;
+  else if (k == "attn_slots") e->opt_attn_slots = value;
+  else if (k == "l2_ahead") e->opt_l2_ahead = value;
+  else if (k == "attn_occ") e->opt_attn_occ = value;
+  else if (k == "cattn_bn") e->opt_cattn_bn = value;
+  else if (k == "ablate") e->opt_ablate = value;
+  else if (k == "detector_precise") e->opt_detector_precise = value;
   else {
     e->err = "unknown option: " + k;
     return 1;
   }
+  e->drop_step_graphs();  // every option may change what a decode step launches: never replay a stale graph
   return 0;
 }
 
@@ -1627,8 +1509,9 @@ int rgrg_generate(rgrg_engine_t* e, const float* images, int images_on_host, int
 }
 
 static const bf16* stage_feats(rgrg_engine* e, const float* feats, int on_host, int R, cudaStream_t st) {
+  const int Rp = rgrg_engine::padded_rows(R);
   e->trf.ensure(static_cast<size_t>(R) * 1024 * 4);
-  e->lm_in.ensure(static_cast<size_t>(R) * 1024 * 2);
+  e->lm_in.ensure(static_cast<size_t>(Rp) * 1024 * 2);
   const float* src = feats;
   if (on_host) {
     CUDA_CHECK(cudaMemcpyAsync(e->trf.p, feats, static_cast<size_t>(R) * 1024 * 4, cudaMemcpyHostToDevice, st));
@@ -1637,6 +1520,7 @@ static const bf16* stage_feats(rgrg_engine* e, const float* feats, int on_host, 
   det::cast_bf16_kernel<<<rgrg_engine::grid_for(static_cast<long long>(R) * 1024), 256, 0, st>>>(src, e->lm_in.as<bf16>(),
                                                                                              static_cast<long long>(R) * 1024);
   KERNEL_CHECK();
+  if (Rp > R) CUDA_CHECK(cudaMemsetAsync(e->lm_in.as<bf16>() + static_cast<size_t>(R) * 1024, 0, static_cast<size_t>(Rp - R) * 1024 * 2, st));
   ++e->launches;
   return e->lm_in.as<bf16>();
 }
@@ -1704,9 +1588,8 @@ int rgrg_lm_forced_logits(rgrg_engine_t* e, const float* feats_dev, int R, const
     g.unfinished_count = e->unf_count.as<int>();
     g.step_ptr = e->step.as<int>();
     g.ticket = e->step.as<int>() + 1;
-    g.advance = 1;
+    g.live_rows = R;
     g.forced = forced_ids_dev;
-    CUDA_CHECK(cudaMemsetAsync(e->ln_counters.p, 0, 64 * 4, st));
     dec::greedy_init_kernel<<<ceil_div(std::max(R, n_tokens), 256), 256, 0, st>>>(g, R);
     KERNEL_CHECK();
     ++e->launches;
@@ -1933,34 +1816,6 @@ int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst, size_t b
     else if (n == "selection_logits") b = &e->sel_logits;
     else if (n == "region_features_2048") b = &e->mean2048;
     else if (n == "fc7") b = &e->f7;
-    else if (n == "grid_sync_cycles") {  // tuning: average cycles of one grid barrier over 200 barriers
-      DevBuf c;
-      c.ensure(256 + 8);
-      CUDA_CHECK(cudaMemset(c.p, 0, 264));
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3(tc::num_sms());
-      cfg.blockDim = dim3(tc::NUM_THREADS);
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeCooperative;
-      attr[0].val.cooperative = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      CUDA_CHECK(cudaLaunchKernelEx(&cfg, mega::grid_sync_bench_kernel, c.as<unsigned>(), 200,
-                                    reinterpret_cast<long long*>(static_cast<char*>(c.p) + 256)));
-      CUDA_CHECK(cudaDeviceSynchronize());
-      long long cyc = 0;
-      CUDA_CHECK(cudaMemcpy(&cyc, static_cast<char*>(c.p) + 256, 8, cudaMemcpyDeviceToHost));
-      c.release();
-      if (bytes < 8) throw std::runtime_error("need 8 bytes");
-      *static_cast<long long*>(host_dst) = cyc / 200;
-      return 0;
-    }
-    else if (n == "mega_trace") {
-      if (bytes > 256 * 8 || !e->mega_sync.p) throw std::runtime_error("no mega trace");
-      CUDA_CHECK(cudaDeviceSynchronize());
-      CUDA_CHECK(cudaMemcpy(host_dst, static_cast<char*>(e->mega_sync.p) + 256, bytes, cudaMemcpyDeviceToHost));
-      return 0;
-    }
     else throw std::runtime_error("unknown debug buffer: " + n);
     if (bytes > b->bytes) throw std::runtime_error("debug read larger than buffer: " + n);
     CUDA_CHECK(cudaDeviceSynchronize());

@@ -34,20 +34,18 @@ struct GemmShape {
   int tiles_w, tiles_h;  // output tiles per image: (W/16) x (H/8); one tile = 8 rows x 16 cols = 128 pixels
   long long* trace;      // optional [grid, 8] clock64 timeline of each CTA (bring-up / tuning only)
   int k_splits;          // split-K factor (0/1 = off): tile index -> (split, m, n); each split covers k_iters / k_splits blocks
-  // Optional tail of a split-K GEMM with one tile per CTA: once all n_tiles * k_splits CTAs of an M tile have stored their
-  // partial sums, each of them reduces + LayerNorms 128 / (n_tiles * k_splits) rows of that M tile (see the kernel).
-  struct LnTail {
-    float* h;             // fp32 residual stream [M, 1024]; null = no tail
+  // Optional LayerNorm head (launched as clusters of 16 CTAs = the 16 N tiles of one M tile, one tile per CTA, m_fastest = 0):
+  // before the main loop CTA `n_blk` reduces the preceding projection's split-K partial sums into the residual stream and
+  // normalises rows [m_blk*128 + n_blk*8, +8) into `x` (this GEMM's own operand A); the cluster meets at barrier.cluster.
+  struct LnHead {
+    float* h;             // fp32 residual stream [M, 1024]; null = no head
+    bf16* x;              // normalised bf16 rows [M, 1024]
     const float* gamma;
     const float* beta;
-    const float* res_bias;  // bias of this projection, added with the partial sums
-    bf16* x;              // normalised bf16 output [M, 1024]
-    const float* parts;   // this GEMM's own partial-sum slices
+    const float* parts;   // split-K partial sums [4][M, 1024] of the preceding projection (null: plain LayerNorm)
     size_t part_stride;
-    unsigned* counters;   // [m_tiles] arrival counters, monotonic within a generate()
-    const int* step_ptr;  // device decode step: targets are derived from it so a captured graph can be replayed
-    int launch_idx, launches_per_step;
-  } ln;
+    const float* res_bias;
+  } lnh;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -230,8 +228,7 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmShape& s, int tile) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The tile pipeline, written as device functions so that both the stand-alone GEMM kernel (below) and the decoder
-// mega-kernel (decoder_megakernel.cuh) run the same code.  A CTA is persistent: it walks tiles blockIdx.x, +gridDim.x,
+// The tile pipeline.  A CTA is persistent: it walks tiles blockIdx.x, +gridDim.x,
 // ...; two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 //   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + MMA issuer (one lane issues tcgen05.mma; tcgen05.commit frees ring slots)
@@ -239,8 +236,7 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmShape& s, int tile) {
 //                 (lane = row) -> swizzled smem transpose -> 8 consecutive columns per lane -> fused epilogue functor
 //                 with 16-byte coalesced global accesses.  (One warp per scheduler cannot hide its own latency: the
 //                 4-warp version of this epilogue needed 14 us for a 128x192 tile, 3x the tile's MMA time.)
-// Ring-slot and accumulator-stage counters (kbg, it) are carried by the caller, so consecutive GEMMs inside one
-// kernel keep the mbarrier phases consistent.
+// Ring-slot and accumulator-stage counters (kbg, it) are carried by the caller.
 // ---------------------------------------------------------------------------------------------------------------
 template <int BN, int STAGES>
 struct Pipe {
@@ -457,46 +453,12 @@ struct Pipe {
   }
 };
 
-// Reduce + LayerNorm tail of a split-K projection (one tile per CTA, all CTAs co-resident: grid <= #SMs).
-// The 16 CTAs that share an M tile meet at a per-M-tile counter; then CTA `rank` owns rows rank*8 .. rank*8+7 of the
-// tile, one row per epilogue warp: h += bias + sum of partial slices, x = LayerNorm(h).  This replaces a separate
-// LayerNorm kernel (one launch + one dependency bubble per projection) by a ~1.5 us group barrier.
-__device__ void ln_row_tail(float* h, const float* gamma, const float* beta, bf16* out, int row, int lane, const float* parts,
-                            size_t part_stride, const float* res_bias, int nparts);
+// one warp: h[row] += bias + split-K partial sums (when parts != null); x[row] = LayerNorm(h[row])   (decoder_kernels.cuh)
+__device__ __forceinline__ void ln_head_row(float* h, const float* gamma, const float* beta, bf16* x, int row, int lane,
+                                            const float* parts, size_t part_stride, const float* res_bias);
 
-__device__ __forceinline__ void ln_tail(const GemmShape& s) {
-  __syncthreads();  // every epilogue warp of this CTA has issued its partial-sum stores
-  const TileCoord tc_ = tile_coord(s, blockIdx.x);
-  const int group = s.n_tiles * s.k_splits;
-  if (threadIdx.x == 0) {
-    const unsigned target =
-        static_cast<unsigned>(*s.ln.step_ptr * s.ln.launches_per_step + s.ln.launch_idx + 1) * static_cast<unsigned>(group);
-    unsigned* ctr = s.ln.counters + tc_.m_blk;
-    unsigned old;
-    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr) : "memory");
-    long long start = clock64();
-    unsigned v = old + 1;
-    while (v < target) {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-      if (clock64() - start > 4000000000LL) {
-        printf("rgrg_b200: LayerNorm-tail group barrier timed out (block %d, count %u, target %u)\n", blockIdx.x, v, target);
-        __trap();
-      }
-    }
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rank = tc_.split * s.n_tiles + tc_.n_blk;
-  const int rows_per_cta = BM / group;
-  if (warp >= 2 && warp - 2 < rows_per_cta) {
-    const int row = tc_.m_blk * BM + rank * rows_per_cta + (warp - 2);
-    if (row < s.M)
-      ln_row_tail(s.ln.h, s.ln.gamma, s.ln.beta, s.ln.x, row, lane, s.ln.parts, s.ln.part_stride, s.ln.res_bias, s.k_splits);
-  }
-}
-
-template <int BN, int STAGES, class Epi>
-__global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int BN, int STAGES, class Epi, bool LN_HEAD = false>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const GemmShape s, const Epi epi) {
   extern __shared__ uint8_t smem_raw[];
@@ -514,22 +476,29 @@ __global__ void __launch_bounds__(NUM_THREADS) gemm_tc_kernel(const __grid_const
   // PDL: everything above overlapped the predecessor's tail; let our own successor get scheduled early as well
   griddep_launch_dependents();
   int kbg = 0, it = 0;
-  if (warp == 0) {
-    if (lane == 0) {
-      // weights never depend on the predecessor kernel: start streaming them before waiting for it
-      const int prefetched = pipe.prefetch_w(&tmB, s, 0);
-      griddep_wait();
-      pipe.produce(&tmA, &tmB, s, kbg, prefetched);
+  // weights never depend on the predecessor kernel: start streaming them before waiting for it
+  int prefetched = 0;
+  if (warp == 0 && lane == 0) prefetched = pipe.prefetch_w(&tmB, s, 0);
+  griddep_wait();
+  if constexpr (LN_HEAD) {
+    // peers' rows become visible at the cluster barrier; operand A is then read through TMA (async proxy): proxy fences
+    const TileCoord t0 = tile_coord(s, blockIdx.x);
+    if (warp >= 2) {
+      const int row = t0.m_blk * BM + t0.n_blk * 8 + (warp - 2);
+      if (row < s.M) ln_head_row(s.lnh.h, s.lnh.gamma, s.lnh.beta, s.lnh.x, row, lane, s.lnh.parts, s.lnh.part_stride, s.lnh.res_bias);
     }
+    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+  }
+  if (warp == 0) {
+    if (lane == 0) pipe.produce(&tmA, &tmB, s, kbg, prefetched);
   } else if (warp == 1) {
-    griddep_wait();
     if (lane == 0) pipe.mma(s, kbg, it, trace);
   } else {
-    griddep_wait();
     pipe.epilogue(s, epi, it, trace);
   }
   if (trace && warp == 2 && lane == 0) trace[5] = clock64();
-  if (s.ln.h) ln_tail(s);
   pipe.teardown();
   if (trace && threadIdx.x == 0) trace[6] = clock64();
 }
@@ -590,19 +559,43 @@ inline int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES, class Epi>
+template <int BN, int STAGES, class Epi, bool LN_HEAD = false>
 inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const Epi& epi,
                    cudaStream_t stream, bool pdl = false) {
   using L = SmemLayout<BN, STAGES>;
-  auto kern = gemm_tc_kernel<BN, STAGES, Epi>;
-  static bool configured = false;  // one static per template instantiation
+  auto kern = gemm_tc_kernel<BN, STAGES, Epi, LN_HEAD>;
+  constexpr int cluster = LN_HEAD ? 16 : 1;
+  static bool configured = false;  // one static per template instantiation; one engine device per process (rgrg_create)
   if (!configured) {
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    if (LN_HEAD) CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     configured = true;
   }
   const int tiles = s.m_tiles * s.n_tiles * (s.k_splits > 1 ? s.k_splits : 1);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  launch_kernel(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, stream, pdl, tmA, tmB, s, epi);
+  // cluster launch (LayerNorm head): one tile per CTA, so that cluster rank == N tile
+  const int grid = cluster > 1 ? tiles : (tiles < num_sms() ? tiles : num_sms());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, s, epi));
 }
 
 }  // namespace tc
