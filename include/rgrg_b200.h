@@ -95,6 +95,12 @@ RGRG_API int rgrg_bbox_features(rgrg_engine_t* e, const float* images, int image
 RGRG_API int rgrg_lm_forced_logits(rgrg_engine_t* e, const float* feats_dev, int R, const int32_t* forced_ids_dev,
                           int n_tokens, float* out_logits_dev, void* stream);
 
+/* greedy-search bookkeeping only (language_model.py:629-650: arg-max, pad-if-finished, EOS tracking, stop rule) driven by
+ * given logits: logits_steps dev fp32 [n_steps, R, 50257]; out_ids host int32 [R, max_length]; out_width = reference width.
+ * Runs the same device kernels and host loop (incl. the every-8-steps exit check) as generate(). */
+RGRG_API int rgrg_greedy_bookkeeping(rgrg_engine_t* e, const float* logits_steps_dev, int n_steps, int R, int max_length,
+                            int32_t* out_ids, int* out_width, void* stream);
+
 /* beam-search bookkeeping only (language_model.py:556-605 + BeamSearchScorer.process / finalize) driven by given logits:
  * logits_steps dev fp32 [n_steps, sentences*num_beams, 50257] (row b of step t is what beam slot b sees at step t);
  * out_ids host int32 [sentences, max_length]; stops early when every sentence is done, like the reference loop. */

@@ -47,6 +47,10 @@ def main():
     imgs = synth.synthetic_images(2, 512, seed=1001)
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
 
+    if only in ("lm_long", "lm_crafted"):
+        lm_only(model, only)
+        return
+
     # ---- selection-based entry: user boxes -> region features (evaluate_bbox_variations.py:92-110), run on the reference's modules
     g = torch.Generator().manual_seed(77)
     ctr = torch.rand(2, 29, 2, generator=g) * 300 + 100
@@ -129,6 +133,75 @@ def main():
     npz("generate_b2.npz", ids=ids_full, selected=selected, class_detected=class_detected,
         top_region_boxes=detections["top_region_boxes"], top_scores=detections["top_scores"],
         backbone_checksum=[float(feats.double().sum()), float(feats.double().abs().sum())])
+
+
+from crafted import BEAM_CASES, GREEDY_CASES, beam_crafted_logits, eos_schedule  # noqa: E402
+
+
+@torch.no_grad()
+def lm_only(model, only):
+    """Decoder-only fixtures.  Inputs: the selected region features of selection.npz (reference output, committed)."""
+    from rgrg_b200 import synth
+
+    lm = model.language_model
+    feats_all = torch.from_numpy(np.load(os.path.join(OUT, "selection.npz"))["selected_features"])
+    if only == "lm_long":
+        # ---- teacher-forced record at real cache lengths: 6 rows x 128 generated tokens (cache length up to 129)
+        rows = feats_all[:6].contiguous()
+        ids = lm.generate(rows, max_length=129)
+        input_ids = ids[:, :1]
+        mask = torch.ones(rows.shape[0], 1, dtype=torch.int64)
+        past = None
+        top_val, top_idx, lse = [], [], []
+        for t in range(ids.shape[1] - 1):
+            mi = lm.prepare_inputs_for_generation(input_ids, past=past, attention_mask=mask, use_cache=True)
+            logits_t, past = lm.forward(**mi, image_hidden_states=rows, return_loss=False)
+            l = logits_t[:, -1, :]
+            v, i = l.topk(8, dim=-1)
+            top_val.append(v); top_idx.append(i.to(torch.int32)); lse.append(torch.logsumexp(l, -1))
+            assert torch.equal(l.argmax(-1), ids[:, t + 1])
+            input_ids = ids[:, : t + 2]
+            mask = torch.ones(rows.shape[0], t + 2, dtype=torch.int64)
+        npz("lm_long.npz", feats=rows, ids=ids.to(torch.int32), top_val=torch.stack(top_val), top_idx=torch.stack(top_idx),
+            logsumexp=torch.stack(lse))
+        return
+    # ---- search loops of the reference driven by GIVEN logits (the model forward is replaced, nothing else):
+    # greedy_search (language_model.py:609-652) and beam_search (:529-607, with oracle/beam_scorer.py)
+    out = {}
+    real_forward = lm.forward
+    for name, (seed, rows, max_length, kind) in GREEDY_CASES.items():
+        steps = max_length - 1
+        mask = eos_schedule(kind, steps, rows)
+        logits = synth.crafted_logits(seed, steps, rows, mask)
+        state = {"t": 0}
+
+        def fake_forward(**kw):
+            t = state["t"]
+            state["t"] += 1
+            return logits[t][:, None, :], ("given",)
+
+        lm.forward = fake_forward
+        ids = lm.generate(torch.zeros(rows, 1024), max_length=max_length)
+        out["greedy_%s_ids" % name] = ids.to(torch.int32)
+        out["greedy_%s_mask" % name] = mask
+        out["greedy_%s_meta" % name] = np.array([seed, rows, max_length], dtype=np.int32)
+        print(name, tuple(ids.shape), "forward calls", state["t"])
+    for name, (seed, sentences, nb, max_length, es, kind) in BEAM_CASES.items():
+        logits = beam_crafted_logits(seed, sentences, nb, max_length, kind)
+        state = {"t": 0}
+
+        def fake_forward(**kw):
+            t = state["t"]
+            state["t"] += 1
+            return logits[t][:, None, :], tuple((torch.zeros(sentences * nb, 1, 1, 1), torch.zeros(sentences * nb, 1, 1, 1)) for _ in range(1))
+
+        lm.forward = fake_forward
+        ids = lm.generate(torch.zeros(sentences, 1024), max_length=max_length, num_beams=nb, early_stopping=es)
+        out["beam_%s_ids" % name] = ids.to(torch.int32)
+        out["beam_%s_meta" % name] = np.array([seed, sentences, nb, max_length, int(es)], dtype=np.int32)
+        print(name, tuple(ids.shape), "forward calls", state["t"])
+    lm.forward = real_forward
+    npz("lm_crafted.npz", **out)
 
 
 if __name__ == "__main__":

@@ -420,9 +420,10 @@ def lm_forward(sd: SD, input_ids: torch.Tensor, image_hidden_states: torch.Tenso
     return F.linear(h, wte), presents  # lm_head tied to wte (:366)
 
 
-def greedy_search(sd: SD, feats: torch.Tensor, max_length: Optional[int], record: Optional[dict] = None
-                  ) -> torch.Tensor:
-    """language_model.py:609-652 (+ prepare_inputs_for_generation :498-520)."""
+def greedy_search(sd: SD, feats: torch.Tensor, max_length: Optional[int], record: Optional[dict] = None,
+                  given_logits: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """language_model.py:609-652 (+ prepare_inputs_for_generation :498-520).  given_logits [steps, rows, V] replaces the
+    model forward (bookkeeping tests)."""
     rows = feats.shape[0]
     ids = torch.full((rows, 1), BOS, dtype=torch.int64)
     mask = torch.ones(rows, 1, dtype=torch.int64)
@@ -433,8 +434,11 @@ def greedy_search(sd: SD, feats: torch.Tensor, max_length: Optional[int], record
         inp = ids if past is None else ids[:, -1:]
         pos = mask.cumsum(-1) - 1
         pos = pos if past is None else pos[:, -1:]
-        logits, past = lm_forward(sd, inp, feats, past, pos, mask)
-        nxt_logits = logits[:, -1, :]
+        if given_logits is not None:
+            nxt_logits = given_logits[cur_len - 1]
+        else:
+            logits, past = lm_forward(sd, inp, feats, past, pos, mask)
+            nxt_logits = logits[:, -1, :]
         if record is not None:
             record.setdefault("logits", []).append(nxt_logits.clone())
         nxt = torch.argmax(nxt_logits, dim=-1)
@@ -448,8 +452,10 @@ def greedy_search(sd: SD, feats: torch.Tensor, max_length: Optional[int], record
     return ids
 
 
-def beam_search(sd: SD, feats: torch.Tensor, max_length: int, num_beams: int, early_stopping: bool) -> torch.Tensor:
-    """language_model.py:529-607 with BeamSearchScorer(length_penalty=1.0, num_beam_hyps_to_keep=1) (:457-464)."""
+def beam_search(sd: SD, feats: torch.Tensor, max_length: int, num_beams: int, early_stopping: bool,
+                given_logits: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """language_model.py:529-607 with BeamSearchScorer(length_penalty=1.0, num_beam_hyps_to_keep=1) (:457-464).
+    given_logits [steps, rows * beams, V] replaces the model forward (bookkeeping tests)."""
     from beam_scorer import BeamSearchScorer
 
     batch = feats.shape[0]
@@ -466,8 +472,12 @@ def beam_search(sd: SD, feats: torch.Tensor, max_length: int, num_beams: int, ea
         inp = ids if past is None else ids[:, -1:]
         pos = mask.cumsum(-1) - 1
         pos = pos if past is None else pos[:, -1:]
-        logits, past = lm_forward(sd, inp, feats, past, pos, mask)
-        scores = F.log_softmax(logits[:, -1, :], dim=-1) + beam_scores[:, None]
+        if given_logits is not None:
+            step_logits = given_logits[cur_len - 1]
+        else:
+            logits, past = lm_forward(sd, inp, feats, past, pos, mask)
+            step_logits = logits[:, -1, :]
+        scores = F.log_softmax(step_logits, dim=-1) + beam_scores[:, None]
         V = scores.shape[-1]
         scores, tokens = torch.topk(scores.view(batch, num_beams * V), 2 * num_beams, dim=1, largest=True, sorted=True)
         indices = torch.div(tokens, V, rounding_mode="floor")
@@ -476,7 +486,8 @@ def beam_search(sd: SD, feats: torch.Tensor, max_length: int, num_beams: int, ea
         beam_scores, beam_tok, beam_idx = out["next_beam_scores"], out["next_beam_tokens"], out["next_beam_indices"]
         ids = torch.cat([ids[beam_idx, :], beam_tok.unsqueeze(-1)], dim=-1)
         mask = torch.cat([mask, mask.new_ones(mask.shape[0], 1)], dim=-1)
-        past = [(k.index_select(0, beam_idx), v.index_select(0, beam_idx)) for k, v in past]  # _reorder_cache :492-496
+        if given_logits is None:
+            past = [(k.index_select(0, beam_idx), v.index_select(0, beam_idx)) for k, v in past]  # _reorder_cache :492-496
         cur_len += 1
         if scorer.is_done or (max_length and cur_len >= max_length):
             break

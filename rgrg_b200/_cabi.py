@@ -23,6 +23,7 @@ _PROTOTYPES = {
     "rgrg_detect": (_i, [c_p, c_p, _i, _i, _i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, C.POINTER(_i), c_p]),
     "rgrg_bbox_features": (_i, [c_p, c_p, _i, _i, _i, c_p, c_p, c_p]),
     "rgrg_lm_forced_logits": (_i, [c_p, c_p, _i, c_p, _i, c_p, c_p]),
+    "rgrg_greedy_bookkeeping": (_i, [c_p, c_p, _i, _i, _i, c_p, C.POINTER(_i), c_p]),
     "rgrg_beam_bookkeeping": (_i, [c_p, c_p, _i, _i, _i, _i, _i, c_p, C.POINTER(_i), c_p]),
     "rgrg_rpn_filter": (_i, [c_p, c_p, c_p, c_p, _i, _i, _i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "rgrg_roi_align": (_i, [c_p, c_p, c_p, c_p, _i, _i, _i, _i, c_p, c_p]),

@@ -34,14 +34,17 @@ constexpr int A_BYTES = tc::BM * tc::BK * 2;   // 16 KB
 constexpr int B_BYTES = BN * tc::BK * 2;       // 24 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int K_ITERS = 1024 / tc::BK;
-constexpr int ATT_WARPS = 8;
 constexpr int TILE_BYTES = tc::BM * 128;       // one 128 x 64 bf16 tile (q, k_new or v_new)
 constexpr int CHUNK_KEYS = 16;
 constexpr int SLOT_BYTES = 2 * CHUNK_KEYS * 128;  // K chunk + V chunk
 constexpr int TMEM_COLS = 256;
 
-template <int NSLOT>
+// AW = attention / epilogue warps per CTA (a multiple of 4: AW / 4 warps share a TMEM lane quarter); block = 64 + 32 AW threads.
+// The per-chunk work of a warp is a chain of dependent shared-memory loads, shuffles and exponentials, so the attention
+// phase scales with the number of resident warps until HBM saturates (measured: 8 warps -> 45 us per layer at 928 rows).
+template <int AW, int NSLOT>
 struct Smem {
+  static constexpr int ATT_WARPS = AW;
   static constexpr int GEMM_BYTES = STAGES * STAGE_BYTES;
   static constexpr int STG_OFFSET = 3 * TILE_BYTES;  // attention phase: tiles at [0, 48 KB), staging rings after them
   static constexpr int ATT_BYTES = STG_OFFSET + ATT_WARPS * NSLOT * SLOT_BYTES;
@@ -83,10 +86,11 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-template <int NSLOT, bool LN_HEAD>
-__global__ void __launch_bounds__(tc::NUM_THREADS, 1) attn_fused_kernel(const __grid_constant__ CUtensorMap tmA,
+template <int AW, int NSLOT, bool LN_HEAD>
+__global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                         const __grid_constant__ CUtensorMap tmW, const Params p) {
-  using L = Smem<NSLOT>;
+  using L = Smem<AW, NSLOT>;
+  constexpr int ATT_WARPS = AW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -135,7 +139,7 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 1) attn_fused_kernel(const __
     // rows [m_blk*128 + head*8, +8) of the M tile: h += bias + split-K partial sums of the preceding projection,
     // x = LayerNorm(h); one row per attention warp.  Peers' rows become visible at the cluster barrier; operand A is read
     // through TMA (async proxy), hence the proxy fences on both sides.
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 10) {
       const int row = m_blk * tc::BM + head * 8 + (warp - 2);
       if (row < p.M) {
         if (p.parts) dec::ln_row_dev<4>(p.h, p.gamma, p.beta, p.x, row, lane, p.parts, p.part_stride, p.res_bias);
@@ -188,12 +192,12 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 1) attn_fused_kernel(const __
     // ---------------------------------------------------------------- epilogue + attention (warps 2..9)
     const int aw = warp - 2;
     const int rows_left = p.M - m_blk * tc::BM;  // valid rows of this M tile (>= 1)
-    // items of this warp: local rows aw, aw + 8, ... (a short last M tile still spreads over all eight warps)
-    const int n_items = rows_left > aw ? min(16, (rows_left - aw + 7) >> 3) : 0;
+    // items of this warp: local rows aw, aw + AW, ... (a short last M tile still spreads over all warps)
+    const int n_items = rows_left > aw ? min((tc::BM - aw + AW - 1) / AW, (rows_left - aw + AW - 1) / AW) : 0;
     const int nsc = (Lc + CHUNK_KEYS - 1) / CHUNK_KEYS;       // staged chunks per item (cached keys)
     const int nchunks = (Ltot + CHUNK_KEYS - 1) / CHUNK_KEYS;  // compute chunks per item (cached + new key)
     const uint32_t blk_bytes = static_cast<uint32_t>(Lc) * 128;
-    auto item_row = [&](int j) { return m_blk * tc::BM + aw + 8 * j; };
+    auto item_row = [&](int j) { return m_blk * tc::BM + aw + AW * j; };
     if (p.l2_ahead > 0 && lane == 0) {
       for (int j = 0; j < p.l2_ahead && j < n_items; ++j) {
         bulk_prefetch_l2(p.kv.cache + p.kv.offset(p.layer, 0, item_row(j), head, 0), blk_bytes);
@@ -206,14 +210,14 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 1) attn_fused_kernel(const __
     tc::tc_fence_after();
     {
       const int q4 = warp & 3;           // TMEM lane quarter this warp may read
-      const int half = aw >> 2;          // which of the two warps of that quarter
+      const int grp = aw >> 2;           // which of the AW / 4 warps of that quarter: takes 16-column chunks grp, grp + AW/4, ...
       const int r = q4 * 32 + lane;      // local row
       const int row = m_blk * tc::BM + r;
       const bool row_ok = row < p.M;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
       const int slot = t + 1;
 #pragma unroll 1
-      for (int c = half * 16; c < BN; c += 32) {
+      for (int c = grp * 16; c < BN; c += 4 * AW) {
         uint32_t v[16];
         tc::tmem_ld_32x32b_x16(t_addr + c, v);
         tc::tmem_ld_wait();
@@ -235,7 +239,7 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 1) attn_fused_kernel(const __
       }
       tc::tc_fence_before();
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");  // all eight warps: tiles complete, the GEMM ring is free for staging
+    asm volatile("bar.sync 1, %0;" ::"r"(32 * AW) : "memory");  // all attention warps: tiles complete, the GEMM ring is free for staging
 
     // ---- attention
     const int sub = lane >> 3, dseg = lane & 7;
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 1) attn_fused_kernel(const __
     for (int s = 0; s < NSLOT && s < total; ++s) issue(s);
     int seq = 0;
     for (int j = 0; j < n_items; ++j) {
-      const int rl = aw + 8 * j;
+      const int rl = aw + AW * j;
       if (p.l2_ahead > 0 && lane == 0 && j + p.l2_ahead < n_items) {
         bulk_prefetch_l2(p.kv.cache + p.kv.offset(p.layer, 0, item_row(j + p.l2_ahead), head, 0), blk_bytes);
         bulk_prefetch_l2(p.kv.cache + p.kv.offset(p.layer, 1, item_row(j + p.l2_ahead), head, 0), blk_bytes);
@@ -351,10 +355,10 @@ __global__ void __launch_bounds__(tc::NUM_THREADS, 1) attn_fused_kernel(const __
   if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int NSLOT, bool LN_HEAD>
+template <int AW, int NSLOT, bool LN_HEAD>
 inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const Params& p, cudaStream_t stream, bool pdl) {
-  using L = Smem<NSLOT>;
-  auto kern = attn_fused_kernel<NSLOT, LN_HEAD>;
+  using L = Smem<AW, NSLOT>;
+  auto kern = attn_fused_kernel<AW, NSLOT, LN_HEAD>;
   static bool configured = false;  // one engine device per process (rgrg_create enforces it)
   if (!configured) {
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
@@ -363,7 +367,7 @@ inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const Params&
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(ceil_div(p.M, tc::BM) * 16);
-  cfg.blockDim = dim3(tc::NUM_THREADS);
+  cfg.blockDim = dim3(64 + 32 * AW);
   cfg.dynamicSmemBytes = L::TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];

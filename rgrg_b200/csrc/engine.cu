@@ -176,9 +176,10 @@ struct rgrg_engine {
   int opt_pdl = 1;
   int opt_detector_precise = 0;  // fp32 detector (parity mode, see run_detect)
   int opt_fused_attn = 1;  // greedy decode: c_attn + KV append + attention as ONE head-aligned kernel (attn_fused.cuh)
-  int opt_ln_head = 1;     // LayerNorm (+ split-K reduce + residual) as the cluster-cooperative head of the consumer GEMM
-  int opt_attn_slots = 4;  // fused attention: shared-memory K/V ring slots per warp (3, 4 or 5)
-  int opt_l2_ahead = 2;    // fused attention: items whose K/V blocks are prefetched into L2 ahead of the consumer
+  int opt_ln_head = 0;     // LayerNorm (+ split-K reduce + residual) as the cluster-cooperative head of the consumer GEMM
+  int opt_attn_warps = 16;  // fused attention: attention / epilogue warps per CTA
+  int opt_attn_slots = 2;  // fused attention: shared-memory K/V ring slots per warp
+  int opt_l2_ahead = 0;    // fused attention: items whose K/V blocks are prefetched into L2 ahead of the consumer
   int opt_cattn_bn = 0;    // tuning: force the N tile of c_attn (0 = pick_bn); two-kernel attention path only
   int opt_attn_occ = 7;    // CTAs per SM the stand-alone attention kernel is compiled for (5: 88 regs, 6: 78, 7: 72, 8: 64)
   int opt_ablate = 0;  // tuning only: bit mask of decode-step kernels to skip (results become meaningless, timing attributes cost)
@@ -908,13 +909,13 @@ struct rgrg_engine {
   int cluster16_ok = -1;
   bool ln_head_available() {
     if (cluster16_ok < 0) {
-      auto kern = fa::attn_fused_kernel<4, true>;
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::Smem<4>::TOTAL);
+      auto kern = fa::attn_fused_kernel<8, 4, true>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::Smem<8, 4>::TOTAL);
       cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(16);
       cfg.blockDim = dim3(tc::NUM_THREADS);
-      cfg.dynamicSmemBytes = fa::Smem<4>::TOTAL;
+      cfg.dynamicSmemBytes = fa::Smem<8, 4>::TOTAL;
       cudaLaunchAttribute attr[1];
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = 16;
@@ -930,12 +931,16 @@ struct rgrg_engine {
     return cluster16_ok > 0;
   }
 
+  // (attention warps, ring slots per warp): 48 KB of q/k/v tiles + AW * NSLOT * 4 KB of K/V staging must fit in 227 KB
   template <bool LN_HEAD>
   void launch_attn_fused(const CUtensorMap& tmA, const CUtensorMap& tmW, const fa::Params& fp, cudaStream_t st) {
-    switch (opt_attn_slots) {
-      case 3: fa::launch<3, LN_HEAD>(tmA, tmW, fp, st, pdl_now); break;
-      case 5: fa::launch<5, LN_HEAD>(tmA, tmW, fp, st, pdl_now); break;
-      default: fa::launch<4, LN_HEAD>(tmA, tmW, fp, st, pdl_now); break;
+    switch (opt_attn_warps * 10 + opt_attn_slots) {
+      case 84: fa::launch<8, 4, LN_HEAD>(tmA, tmW, fp, st, pdl_now); break;
+      case 123: fa::launch<12, 3, LN_HEAD>(tmA, tmW, fp, st, pdl_now); break;
+      case 161: fa::launch<16, 1, LN_HEAD>(tmA, tmW, fp, st, pdl_now); break;
+      case 162: fa::launch<16, 2, LN_HEAD>(tmA, tmW, fp, st, pdl_now); break;
+      case 241: fa::launch<24, 1, LN_HEAD>(tmA, tmW, fp, st, pdl_now); break;
+      default: throw std::runtime_error("unsupported (attn_warps, attn_slots): 8/4, 12/3, 16/1, 16/2, 24/1");
     }
   }
 
@@ -1253,11 +1258,14 @@ struct rgrg_engine {
   // number of selected regions differs by a few rows replay the same graph (rows never interact; padded rows start
   // "finished", emit EOS and are not counted).
   static int padded_rows(int R) { return (R + 31) & ~31; }
-  int run_greedy(const bf16* feats_bf16, int R, int max_length, int32_t* out_ids, cudaStream_t st) {
-    const int Rp = padded_rows(R);
+  // injected_logits != null (tests): the model forward is replaced by given logits [steps, R, V]; everything else — the
+  // device-side greedy bookkeeping, the every-8-steps exit check, the width rule — is the code generate() runs.
+  int run_greedy(const bf16* feats_bf16, int R, int max_length, int32_t* out_ids, cudaStream_t st,
+                 const float* injected_logits = nullptr, int injected_steps = 0) {
+    const int Rp = injected_logits ? R : padded_rows(R);
     ensure_decoder_ws(Rp, max_length);
     if (opt_gemm_impl == 2) logits_tmp.ensure(static_cast<size_t>(Rp) * VOCAB * 4);
-    lm_prologue(feats_bf16, Rp, 1, st);
+    if (!injected_logits) lm_prologue(feats_bf16, Rp, 1, st);
     dec::GreedyState g{};
     g.ids = ids.as<int>();
     g.ids_ld = max_length;
@@ -1273,9 +1281,18 @@ struct rgrg_engine {
     cudaGraphExec_t exec = nullptr;
     int nodes = 0;
     const int graph_key = Rp * 4096 + max_length;
+    int inj_t = 0;
+    auto step_fn = [&]() {
+      if (!injected_logits) return decode_step(Rp, g, nullptr, st);
+      if (inj_t >= injected_steps) throw std::runtime_error("not enough injected logit steps");
+      launch_kernel(dec::greedy_update_kernel, dim3(ceil_div(Rp, 8)), dim3(256), 0, st, false, static_cast<const float*>(nullptr),
+                    static_cast<const int*>(nullptr), 0, injected_logits + static_cast<size_t>(inj_t++) * R * VOCAB, g, Rp);
+      ++launches;
+      return 1;
+    };
     // step 0 always runs eagerly (it also makes sure every kernel is loaded and configured before a capture)
-    decode_step(Rp, g, nullptr, st);
-    if (opt_cuda_graph && !prof_on && steps > 1) {
+    if (steps > 0) step_fn();
+    if (opt_cuda_graph && !prof_on && steps > 1 && !injected_logits) {
       auto it = step_graphs.find(graph_key);
       if (it == step_graphs.end()) {
         cudaGraph_t graph;
@@ -1306,7 +1323,7 @@ struct rgrg_engine {
         CUDA_CHECK(cudaGraphLaunch(exec, st));
         launches += nodes;
       } else {
-        decode_step(Rp, g, nullptr, st);
+        step_fn();
       }
       ++done_steps;
       if ((t & 7) == 7 && t + 1 < steps) {  // early exit without a per-step sync (language_model.py:649)
@@ -1427,6 +1444,7 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "fused_attn") e->opt_fused_attn = value;
   else if (k == "ln_head") e->opt_ln_head = value;
   else if (k == "attn_slots") e->opt_attn_slots = value;
+  else if (k == "attn_warps") e->opt_attn_warps = value;
   else if (k == "l2_ahead") e->opt_l2_ahead = value;
   else if (k == "attn_occ") e->opt_attn_occ = value;
   else if (k == "cattn_bn") e->opt_cattn_bn = value;
@@ -1595,6 +1613,16 @@ int rgrg_lm_forced_logits(rgrg_engine_t* e, const float* feats_dev, int R, const
     ++e->launches;
     for (int t = 0; t < n_tokens; ++t) e->decode_step(R, g, out_logits_dev + static_cast<size_t>(t) * R * VOCAB, st);
     CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int rgrg_greedy_bookkeeping(rgrg_engine_t* e, const float* logits_steps_dev, int n_steps, int R, int max_length, int32_t* out_ids,
+                            int* out_width, void* stream) {
+  RGRG_TRY(e, {
+    cudaStream_t st = e->enter(stream);
+    if (R <= 0 || max_length < 2) throw std::runtime_error("R must be positive and max_length >= 2");
+    const int width = e->run_greedy(nullptr, R, max_length, out_ids, st, logits_steps_dev, n_steps);
+    if (out_width) *out_width = width;
   });
 }
 
@@ -1816,6 +1844,12 @@ int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst, size_t b
     else if (n == "selection_logits") b = &e->sel_logits;
     else if (n == "region_features_2048") b = &e->mean2048;
     else if (n == "fc7") b = &e->f7;
+    else if (n == "cluster16_max_active") {
+      if (bytes < 4) throw std::runtime_error("need 4 bytes");
+      e->ln_head_available();
+      *static_cast<int*>(host_dst) = e->cluster16_ok;
+      return 0;
+    }
     else throw std::runtime_error("unknown debug buffer: " + n);
     if (bytes > b->bytes) throw std::runtime_error("debug read larger than buffer: " + n);
     CUDA_CHECK(cudaDeviceSynchronize());

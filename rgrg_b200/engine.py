@@ -151,6 +151,14 @@ class Engine:
                                                     _stream(self.device)))
         return out
 
+    def greedy_bookkeeping(self, logits_steps: torch.Tensor, max_length: int):
+        n_steps, R = int(logits_steps.shape[0]), int(logits_steps.shape[1])
+        ids = np.full((R, max_length), EOS, dtype=np.int32)
+        width = C.c_int(0)
+        self._check(self._lib.rgrg_greedy_bookkeeping(self._h, _ptr(logits_steps.contiguous()), n_steps, R, max_length,
+                                                      _ptr(ids), C.byref(width), _stream(self.device)))
+        return ids[:, : width.value]
+
     def beam_bookkeeping(self, logits_steps: torch.Tensor, sentences: int, num_beams: int, max_length: int,
                          early_stopping: bool):
         n_steps = int(logits_steps.shape[0])

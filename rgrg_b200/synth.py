@@ -238,3 +238,17 @@ def synthetic_images(batch: int, size: int = 512, seed: int = 1000) -> torch.Ten
     """N(0,1) pixels ~ the distribution after Normalize(mean .471, std .302)
     (generate_reports_for_images.py:29-30,138)."""
     return torch.randn(batch, 1, size, size, generator=torch.Generator().manual_seed(seed))
+
+
+def crafted_logits(seed: int, steps: int, rows: int, eos_mask=None, eos_logit: float = 14.0, scale: float = 2.0) -> torch.Tensor:
+    """Seeded logits [steps, rows, 50257] for the bookkeeping tests (greedy / beam loops driven by GIVEN logits instead
+    of the model forward): N(0, scale^2) base, EOS (50256) raised to `eos_logit` where eos_mask[t, r] is set.  The same
+    function builds the golden vectors (oracle/make_golden.py, through the reference's own search loops) and the
+    inputs of the GPU tests."""
+    g = torch.Generator().manual_seed(seed)
+    logits = torch.randn(steps, rows, VOCAB, generator=g) * scale
+    if eos_mask is not None:
+        m = torch.as_tensor(eos_mask, dtype=torch.bool)
+        logits[:, :, VOCAB - 1] = torch.where(m, torch.full_like(logits[:, :, 0], eos_logit), logits[:, :, VOCAB - 1])
+    return logits
+

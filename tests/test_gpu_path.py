@@ -142,15 +142,15 @@ def test_fused_attention_is_bit_identical_to_two_kernel_attention(model, oracle_
     _opts(eng, ln_head=0, fused_attn=0)
     ref = eng.lm_generate(feats, 36)
     try:
-        for slots in (4, 3, 5):
+        for warps, slots in ((8, 4), (12, 3), (16, 1), (16, 2), (24, 1)):
             for ahead in (0, 2):
-                _opts(eng, fused_attn=1, attn_slots=slots, l2_ahead=ahead)
+                _opts(eng, fused_attn=1, attn_warps=warps, attn_slots=slots, l2_ahead=ahead)
                 out = eng.lm_generate(feats, 36)
-                assert np.array_equal(ref, out), "slots=%d l2_ahead=%d" % (slots, ahead)
+                assert np.array_equal(ref, out), "warps=%d slots=%d l2_ahead=%d" % (warps, slots, ahead)
         _opts(eng, cuda_graph=0)
         assert np.array_equal(ref, eng.lm_generate(feats, 36))
     finally:
-        _opts(eng, cuda_graph=1, fused_attn=1, attn_slots=4, l2_ahead=2, ln_head=1)
+        _opts(eng, cuda_graph=1, fused_attn=1, attn_warps=16, attn_slots=2, l2_ahead=2, ln_head=0)
 
 
 def test_layernorm_head_matches_separate_layernorm(model, oracle_detail):
@@ -169,7 +169,7 @@ def test_layernorm_head_matches_separate_layernorm(model, oracle_detail):
         _opts(eng, cuda_graph=1, fused_attn=0)  # head on c_fc only, two-kernel attention
         d = eng.lm_generate(feats, 16)
     finally:
-        _opts(eng, cuda_graph=1, fused_attn=1, ln_head=1)
+        _opts(eng, cuda_graph=1, fused_attn=1, ln_head=0)
     assert np.array_equal(b, c) and np.array_equal(b, d)
     assert np.array_equal(a[:, :4], b[:, :4]) and (a == b).mean() > 0.9
 

@@ -67,6 +67,44 @@ def test_lm_greedy_matches_reference(golden, lm_sd):
         assert torch.allclose(torch.logsumexp(logits, -1), T(g["logsumexp"][t]), rtol=0, atol=2e-5)
 
 
+def test_lm_long_teacher_forced_matches_reference(golden, lm_sd):
+    """Decoder at real cache lengths (up to 129 keys): the reference's own 128-step greedy decode, re-run teacher-forced
+    through the oracle's cached forward; logits agree to fp32 noise at every step."""
+    g = golden("lm_long.npz")
+    feats, ids = T(g["feats"]), T(g["ids"]).long()
+    rows = feats.shape[0]
+    past = None
+    with torch.no_grad():
+        for t in range(ids.shape[1] - 1):
+            pos = torch.full((rows, 1), t, dtype=torch.int64)
+            mask = torch.ones(rows, t + 1, dtype=torch.int64)
+            logits, past = O.lm_forward(lm_sd, ids[:, t:t + 1], feats, past, pos, mask)
+            l = logits[:, -1, :]
+            ref_idx = T(g["top_idx"][t]).long()
+            assert torch.allclose(l.gather(1, ref_idx), T(g["top_val"][t]), rtol=0, atol=5e-5), t
+            assert torch.allclose(torch.logsumexp(l, -1), T(g["logsumexp"][t]), rtol=0, atol=5e-5), t
+            assert torch.equal(l.argmax(-1), ids[:, t + 1]), t
+
+
+def test_search_loops_on_crafted_logits_match_reference(golden):
+    """greedy_search / beam_search bookkeeping (pad-if-finished, stop rule, width; beam ties, EOS beyond rank num_beams,
+    simultaneous finishes) against ids the UNMODIFIED reference loops produced from the same crafted logits."""
+    import crafted
+    from rgrg_b200 import synth
+
+    g = golden("lm_crafted.npz")
+    for name, (seed, rows, max_length, kind) in crafted.GREEDY_CASES.items():
+        mask = crafted.eos_schedule(kind, max_length - 1, rows)
+        assert np.array_equal(mask.numpy(), g["greedy_%s_mask" % name])
+        logits = synth.crafted_logits(seed, max_length - 1, rows, mask)
+        ids = O.greedy_search({}, torch.zeros(rows, 1024), max_length, given_logits=logits)
+        assert torch.equal(ids, T(g["greedy_%s_ids" % name]).long()), name
+    for name, (seed, sentences, nb, max_length, es, kind) in crafted.BEAM_CASES.items():
+        logits = crafted.beam_crafted_logits(seed, sentences, nb, max_length, kind)
+        ids = O.beam_search({}, torch.zeros(sentences, 1024), max_length, nb, es, given_logits=logits)
+        assert torch.equal(ids, T(g["beam_%s_ids" % name]).long()), name
+
+
 def test_lm_beam_matches_reference(golden, lm_sd):
     for es in (True, False):
         g = golden("lm_beam_es%d.npz" % int(es))

@@ -30,22 +30,24 @@ def run(mask=0, **opts):
 
 
 print("rows %d, T %d" % (ROWS, T), flush=True)
+import numpy as np
+print("max active 16-CTA clusters:", int(eng.debug_read("cluster16_max_active", (1,), np.int32)[0]), flush=True)
+eng.set_option("ln_head", 0)
 base = run(0)
-print("full step (fused attention + LayerNorm heads): %.3f ms" % base, flush=True)
+print("full step (fused attention, separate LayerNorm): %.3f ms" % base, flush=True)
 if "variants" in sys.argv:
-    print("  ln_head=0                         : %.3f ms" % run(0, ln_head=0), flush=True)
-    print("  ln_head=0 fused_attn=0 (round 1)  : %.3f ms" % run(0, fused_attn=0), flush=True)
-    print("  ln_head=1 fused_attn=0            : %.3f ms" % run(0, ln_head=1), flush=True)
-    eng.set_option("fused_attn", 1)
-    for slots in (3, 5, 4):
-        print("  attn_slots=%d                      : %.3f ms" % (slots, run(0, attn_slots=slots)), flush=True)
-    for ahead in (0, 1, 4, 8, 2):
-        print("  l2_ahead=%d                        : %.3f ms" % (ahead, run(0, l2_ahead=ahead)), flush=True)
+    for aw, sl in ((8, 4), (12, 3), (16, 1), (24, 1), (16, 2)):
+        for ahead in (0, 2):
+            print("  attn_warps=%d attn_slots=%d l2_ahead=%d : %.3f ms" % (aw, sl, ahead, run(0, attn_warps=aw, attn_slots=sl, l2_ahead=ahead)), flush=True)
+    print("  fused_attn=0 (round 1 step)       : %.3f ms" % run(0, fused_attn=0), flush=True)
+    print("  fused_attn=0 ln_head=1            : %.3f ms" % run(0, ln_head=1), flush=True)
+    print("  fused_attn=1 ln_head=1            : %.3f ms" % run(0, fused_attn=1), flush=True)
+    eng.set_option("ln_head", 0)
     print("  PDL off                           : %.3f ms" % run(0, pdl=0), flush=True)
     print("  eager, no graph                   : %.3f ms" % run(0, pdl=1, cuda_graph=0), flush=True)
     eng.set_option("cuda_graph", 1)
-configs = [("attn_fused (+LN1 head)", 64), ("attn_c_proj", 8), ("mlp_c_fc (+LN2 head)", 16), ("mlp_c_proj", 32),
-           ("everything in the layers", 64 | 8 | 16 | 32)]
+configs = [("attn_fused", 64), ("layernorm", 2), ("attn_c_proj", 8), ("mlp_c_fc", 16), ("mlp_c_proj", 32),
+           ("everything in the layers", 64 | 2 | 8 | 16 | 32)]
 for name, mask in configs:
     t = run(mask)
     print("without %-24s: %.3f ms  (saves %.3f ms = %.1f us per layer)" % (name, t, base - t, (base - t) / 24 * 1e3), flush=True)
