@@ -15,8 +15,9 @@ Prints ONE JSON line on rank 0.
   roofline    the dominant kernel category, timed live with CUDA events on the launch stream (engine "profile"
               option) against MEASURED_PEAKS.json
   cpu_baseline / --impl reference
-              the CPU restatement of the reference's own algorithm (oracle/, kind "port": the reference is Python and
-              cannot travel to the GPU box) timed on the box's host cores on a bounded sample (1 image, same T)
+              the reference's own CPU implementation of the path on the box's host cores: the UNMODIFIED reference
+              files (oracle/_ref/, kind "reference") when the build container has installed them, else the oracle
+              port (kind "port"); a bounded sample of the workload (1-4 images per step, same T, full generate())
 """
 from __future__ import annotations
 
@@ -108,52 +109,45 @@ def log(msg):
         print("[bench %s] %s" % (time.strftime("%H:%M:%S"), msg), file=sys.stderr, flush=True)
 
 
-def timed_oracle_generate(sd, img, T, decode_budget_s=25.0):
-    """The reference's CPU algorithm (oracle port) on one batch, with a BOUNDED decode: the greedy loop
-    (language_model.py:609-652 as restated by rgrg_oracle.lm_forward) is stepped until T-1 steps are done or the
-    budget is spent; the remaining steps are extrapolated with a least-squares line through the measured per-step
-    times (the reference regrows the KV cache with torch.cat every step, so step time grows linearly with t).
-    Returns (seconds for the whole generate(), description)."""
-    import numpy as np
+def load_cpu_reference(sd):
+    """The CPU implementation of the path that the CPU legs time: the UNMODIFIED reference (oracle/_ref/, copied by
+    oracle/install_ref.py in the build container; `kind: "reference"`) or, when that is absent, the oracle port
+    (`kind: "port"`).  Returns (kind, generate(images, max_length) -> output, threads)."""
     import torch
 
-    import rgrg_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: undo it for the CPU arm
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import ref_harness
 
+        if not ref_harness.reference_available():
+            raise RuntimeError("no reference checkout")
+        model = ref_harness.build_reference_model(None)
+        missing, unexpected = model.load_state_dict(sd, strict=False)
+        assert not unexpected, unexpected[:3]
+        model.eval()
+
+        def gen(images, T):
+            with torch.no_grad():
+                return model.generate(images, max_length=T)
+
+        return "reference", gen, torch.get_num_threads()
+    except Exception as exc:  # noqa: BLE001 - any import / build problem -> the port, stated in the output
+        log("reference not usable (%s): timing the oracle port" % (str(exc).splitlines()[0] if str(exc) else type(exc).__name__))
+        import rgrg_oracle as O
+
+        def gen(images, T):
+            return O.generate(sd, images, max_length=T)
+
+        return "port", gen, torch.get_num_threads()
+
+
+def timed_cpu_generate(gen, images, T):
     t0 = time.perf_counter()
-    with torch.no_grad():
-        det = O.detect(sd, img)
-        selected, feats, _ = O.region_selection(sd, det["top_region_features"], det["class_detected"])
-    t_det = time.perf_counter() - t0
-    R = int(feats.shape[0])
-    step_times = []
-    if R > 0:
-        ids = torch.full((R, 1), O.BOS, dtype=torch.int64)
-        mask = torch.ones(R, 1, dtype=torch.int64)
-        past = None
-        with torch.no_grad():
-            for t in range(T - 1):
-                ts = time.perf_counter()
-                inp = ids if past is None else ids[:, -1:]
-                pos = mask.cumsum(-1) - 1
-                pos = pos if past is None else pos[:, -1:]
-                logits, past = O.lm_forward(sd, inp, feats, past, pos, mask)
-                nxt = torch.argmax(logits[:, -1, :], dim=-1)
-                ids = torch.cat([ids, nxt[:, None]], dim=-1)
-                mask = torch.cat([mask, mask.new_ones(R, 1)], dim=-1)
-                step_times.append(time.perf_counter() - ts)
-                if sum(step_times) > decode_budget_s and len(step_times) >= 4:
-                    break
-    n = len(step_times)
-    t_dec = sum(step_times)
-    extrap = ""
-    if 0 < n < T - 1:
-        xs = np.arange(n, dtype=np.float64)
-        a, b = np.polyfit(xs[1:], np.array(step_times[1:]), 1) if n > 2 else (0.0, step_times[-1])
-        rest = np.arange(n, T - 1, dtype=np.float64)
-        t_dec += float(np.sum(np.maximum(a * rest + b, step_times[-1])))
-        extrap = ", %d of %d decode steps measured, rest extrapolated linearly" % (n, T - 1)
-    desc = "%d image(s), R=%d rows, detector %.1f s + decoder %.1f s%s" % (img.shape[0], R, t_det, t_dec, extrap)
-    return t_det + t_dec, R, desc
+    out = gen(images, T)
+    dt = time.perf_counter() - t0
+    R = 0 if isinstance(out, int) else int(out[0].shape[0])
+    return dt, R
 
 
 def flops_per_image(S, P, R, T):
@@ -185,45 +179,61 @@ def category_bytes(cat, rows, mean_L):
     """algorithmic HBM bytes of one launch of the HBM-bound categories."""
     if cat == "attention":
         return rows * mean_L * 2 * 1024 * 2.0  # K and V rows of one layer, bf16
+    if cat == "attn_fused":
+        # fused c_attn + KV append + attention: cached K / V rows read (mean_L - 1 keys) + the appended k, v + q-side
+        # operands (x read, attention output written) + the layer's c_attn weight
+        return rows * (mean_L - 1) * 4096.0 + rows * 4096.0 + rows * 1024 * 2 * 2.0 + 3072 * 1024 * 2.0
     if cat == "layernorm":
         return rows * 1024 * (4 + 2.0)
     return None
 
 
+def ncu_traffic(cat):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the category's kernel, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json records the figure, the launch it was taken on and the report)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        return t.get(cat)
+    except Exception:
+        return None
+
+
 def run_reference_arm(args, rank, world):
-    """--impl reference: the reference's CPU algorithm (oracle port) on the host cores; rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores; rank 0 only.  Every step
+    is one full `generate()` (no time-boxing, no extrapolation) on a bounded sample of the workload: `b` images per
+    step, with b chosen after the first warm-up step so that the whole run stays within a few minutes."""
     if rank != 0:
         return
-    import torch
-
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import rgrg_oracle as O
-
     from rgrg_b200 import synth
 
     sd = synth.make_state_dict(0)
+    kind, gen, cores = load_cpu_reference(sd)
     T = args.max_length
+    n_steps = args.warmup + args.steps
+    budget = 360.0 / max(1, n_steps)  # seconds per step
+    b = 1
     times = []
-    desc = ""
-    # every step is a bounded sample (1 image; decode time-boxed) so that W + K steps end within a few minutes
-    budget = max(4.0, min(25.0, 200.0 / max(1, args.warmup + args.steps) - 4.0))
-    for step in range(args.warmup + args.steps):
-        img = synth.synthetic_images(1, args.image_size, seed=2000 + step)
-        dt, R_seen, desc = timed_oracle_generate(sd, img, T, decode_budget_s=budget)
-        log("reference step %d: %.1f s (%s)" % (step, dt, desc))
+    R_seen = 0
+    for step in range(n_steps):
+        img = synth.synthetic_images(b, args.image_size, seed=2000 + step)
+        dt, R_seen = timed_cpu_generate(gen, img, T)
+        log("reference step %d: %.1f s (%d image(s), R=%d rows)" % (step, dt, b, R_seen))
         if step >= args.warmup:
             times.append(dt)
+        elif step == 0 and args.warmup >= 1:
+            b = int(max(1, min(4, budget // max(dt, 1e-3))))  # fixed from here on: every timed step uses the same b
     total = sum(times)
-    value = len(times) * 1.0 / total
-    cores = torch.get_num_threads()
-    sample = "1 image / step, %dx%d, greedy max_length=%d, fp32 oracle port of the reference algorithm; last step: %s" % (
-        args.image_size, args.image_size, T, desc)
+    value = len(times) * b / total
+    what = "the UNMODIFIED reference (oracle/_ref)" if kind == "reference" else "fp32 oracle port of the reference algorithm"
+    sample = "%d image(s) per step (of the %d-image workload batch), %dx%d, greedy max_length=%d, %s, fp32 CPU, full generate() per step; last step R=%d rows" % (
+        b, args.batch, args.image_size, args.image_size, T, what, R_seen)
+    cfg = workload_config(args, args.batch, world)
+    cfg["timed_batch_per_step"] = b  # what this arm actually times per step; `workload` names the GPU arm's configuration
     line = {
         "impl": "reference", "metric": "reports_per_sec", "value": value, "unit": "reports/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.batch, world),  # the SAME workload as the GPU arm; `sample` says what was timed
-        "cpu_baseline": {"value": value, "unit": "reports/s", "cores": cores, "kind": "port", "sample": sample},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": "reports/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "reports/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -231,28 +241,31 @@ def run_reference_arm(args, rank, world):
 
 
 def workload_config(args, batch_per_gpu, world):
-    return {"workload": "ReportGenerationModel.generate: %dx%d synthetic grayscale, batch %d per GPU, greedy, 29 regions, "
-                        "max_length %d (BASELINE.json configs[1])" % (args.image_size, args.image_size, batch_per_gpu, args.max_length),
+    mode = "greedy" if args.num_beams == 1 else "beam search x%d%s" % (args.num_beams, ", early stopping" if args.early_stopping else "")
+    which = ("configs[1]" if (args.num_beams == 1 and args.max_length == 64 and args.image_size == 512 and batch_per_gpu == 32) else
+             "configs[2]" if (args.num_beams == 1 and args.max_length == 128 and args.image_size == 512) else
+             "configs[3]" if (args.num_beams == 4 and args.max_length == 128) else
+             "configs[4]" if args.image_size == 1024 else "variant")
+    return {"workload": "ReportGenerationModel.generate: %dx%d synthetic grayscale, batch %d per GPU, %s, 29 regions, "
+                        "max_length %d (BASELINE.json %s)" % (args.image_size, args.image_size, batch_per_gpu, mode, args.max_length, which),
             "global_batch": batch_per_gpu * world, "image_size": args.image_size, "max_length": args.max_length,
+            "num_beams": args.num_beams,
             "parallelism": "images sharded over %d GPU(s), no data-path collective; 1 NCCL all-gather of token buffers per step" % world,
             "weights": "rgrg_b200.synth seed 0 (conditioned random init, SURVEY.md §8(d))",
             "l2": "per-step working set (KV cache + weights + RoI features > 10 GB) >> 126 MB L2; input batch alternates between two seeds"}
 
 
 def cpu_baseline(args, sd):
-    """Bounded CPU sample on rank 0: the oracle port on 1 image of the same workload."""
-    import torch
-
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import rgrg_oracle as O
-
+    """Bounded CPU sample on rank 0: ONE image of the same workload through the reference's own generate()."""
     from rgrg_b200 import synth
 
+    kind, gen, cores = load_cpu_reference(sd)
     img = synth.synthetic_images(1, args.image_size, seed=2000)
-    dt, R, desc = timed_oracle_generate(sd, img, args.max_length, decode_budget_s=20.0)
-    return {"value": 1.0 / dt, "unit": "reports/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "%dx%d, greedy max_length=%d, fp32 oracle port of the reference algorithm: %s"
-                      % (args.image_size, args.image_size, args.max_length, desc)}
+    dt, R = timed_cpu_generate(gen, img, args.max_length)
+    what = "the UNMODIFIED reference (oracle/_ref)" if kind == "reference" else "fp32 oracle port of the reference algorithm"
+    return {"value": 1.0 / dt, "unit": "reports/s", "cores": cores, "kind": kind,
+            "sample": "1 image, %dx%d, greedy max_length=%d, %s, fp32 CPU, one full generate(): %.1f s, R=%d rows"
+                      % (args.image_size, args.image_size, args.max_length, what, dt, R)}
 
 
 def main():
@@ -264,6 +277,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--max-length", type=int, default=64)
     ap.add_argument("--image-size", type=int, default=512)
+    ap.add_argument("--num-beams", type=int, default=1, help="beam search width (BASELINE.json configs[3] uses 4)")
+    ap.add_argument("--early-stopping", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -320,12 +335,13 @@ def main():
         return parallel.all_gather_results(out, B, T, device=dev)
 
     def step_device(i):
-        out = eng.generate(dev_batches[i % 2], T)
+        out = eng.generate(dev_batches[i % 2], T, args.num_beams, args.early_stopping)
         collect(out)
         return out
 
     def step_e2e(i):
-        out = model.generate(host_batches[i % 2], max_length=T)  # reference-facing call, host images
+        out = model.generate(host_batches[i % 2], max_length=T, num_beams=args.num_beams,
+                             early_stopping=args.early_stopping)  # reference-facing call, host images
         if out != -1:
             ids = out[0]
             _ = ids.cpu()  # D2H read of the result, as the reference's caller does before tokenizer.batch_decode
@@ -390,7 +406,7 @@ def main():
     if rank == 0:
         peaks = load_peaks()
         eng.set_option("profile", 1)
-        eng.generate(dev_batches[0], T)
+        eng.generate(dev_batches[0], T, args.num_beams, args.early_stopping)
         prof = eng.profile_read()
         eng.set_option("profile", 0)
         P_total = int(sum(eng.detect(dev_batches[0])["num_proposals"]))
@@ -404,8 +420,8 @@ def main():
         # The eager per-launch events include launch gaps that the timed region (CUDA-graph replay) does not pay.  For the
         # decode-step kernels, re-measure the dominant category under graph replay by ablation: decode-only time with and
         # without that category, CUDA events on the launch stream, difference / launches.
-        ABLATE = {"attention": 1, "layernorm": 2, "c_attn": 4, "attn_c_proj": 8, "mlp_c_fc": 16, "mlp_c_proj": 32}
-        if top in ABLATE and R > 0:
+        ABLATE = {"attention": 1, "layernorm": 2, "c_attn": 4, "attn_c_proj": 8, "mlp_c_fc": 16, "mlp_c_proj": 32, "attn_fused": 64}
+        if top in ABLATE and R > 0 and args.num_beams == 1:
             det = eng.detect(dev_batches[0])
             feats = torch.from_numpy(det["region_features"][det["selected"]]).to(dev)
 
@@ -430,28 +446,35 @@ def main():
             achieved = fl / (avg_ms / 1e3) / 1e12
             peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
             roofline = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                        "frac": achieved / peak, "traffic": None, "peak_source": peaks["_source"] + " (sustained bf16 GEMM)",
+                        "frac": achieved / peak, "traffic": (ncu_traffic(top) or {}).get("bytes_per_launch"),
+                        "peak_source": peaks["_source"] + " (sustained bf16 GEMM)",
                         "launches": n, "avg_ms": avg_ms, "timing": timing}
         else:
             by = category_bytes(top, R, (T + 2) / 2.0)
             if by is not None:
                 achieved = by / (avg_ms / 1e3) / 1e9
                 roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["_source"],
-                            "launches": n, "avg_ms": avg_ms, "timing": timing,
-                            "note": "algorithmic bytes = rows x mean L x 4096 B (K and V rows of one layer); ncu at L = 60: "
-                                    "230 MB in 48 us (dram__bytes_read = algorithmic bytes), profiles/r01_decode_experiments.md"}
+                            "frac": achieved / peaks["hbm_gbs"], "traffic": (ncu_traffic(top) or {}).get("bytes_per_launch"),
+                            "traffic_note": (ncu_traffic(top) or {}).get("note"), "peak_source": peaks["_source"],
+                            "launches": n, "avg_ms": avg_ms, "timing": timing, "algorithmic_bytes_per_launch": by,
+                            "note": "algorithmic bytes per launch = rows x (mean L - 1) x 4096 B cached K/V read + rows x 4096 B "
+                                    "appended + x / attention-output rows + the c_attn weight (DESIGN.md §4), mean L over the T - 1 steps"}
 
     if rank == 0:
         P_est = P_total / B if breakdown is not None else 850
-        whole = flops_per_image(S, P_est, R / B, T) * B * world * args.steps / (ms_max / 1e3) / 1e12
+        whole = flops_per_image(S, P_est, R * args.num_beams / B, T) * B * world * args.steps / (ms_max / 1e3) / 1e12
+        peaks = load_peaks()
+        tensor_peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) * world
         line = {
             "metric": "reports_per_sec", "value": value, "unit": "reports/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline,
-            "whole_path": {"algorithmic_tflops": whole, "rows_per_gpu": R, "proposals_per_image": P_est},
+            "whole_path": {"algorithmic_tflops": whole, "frac": whole / tensor_peak, "peak_tflops": tensor_peak,
+                           "peak_source": peaks["_source"] + " (sustained bf16 GEMM x n_gpus)", "rows_per_gpu": R * args.num_beams,
+                           "proposals_per_image": P_est,
+                           "note": "fraction of the conv + GEMM roofline: SURVEY.md §8(d) algorithmic FLOPs of the whole path / step time"},
             "kernel_breakdown": breakdown,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -127,7 +127,8 @@ RGRG_API int rgrg_roi_tail(rgrg_engine_t* e, const float* class_logits_dev, cons
 
 /* D[M,N] (fp32 dev) = A[M,K] (bf16 dev) * W[N,K]^T (bf16 dev) + bias[N] (fp32 dev or NULL).
  * impl: 0 / 1 / 3 / 4 = tcgen05 with N tile 128 / 64 / 192 / 256, 5 = tcgen05 with the engine's own tile choice,
- *       2 = CUDA-core cross-check.  act: 0 none, 1 relu, 2 gelu_new. */
+ *       2 = CUDA-core cross-check, 6 = the decoder's split-K form (4 K slices -> fp32 partial sums -> reduce, act must be 0).
+ *       act: 0 none, 1 relu, 2 gelu_new. */
 RGRG_API int rgrg_gemm_bf16(rgrg_engine_t* e, const void* A_dev, const void* W_dev, const float* bias_dev, int M, int N, int K,
                    int act, int impl, float* out_dev, void* stream);
 

@@ -74,7 +74,7 @@ def beam_crafted_logits(seed, sentences, nb, max_length, kind):
         for t in range(1, steps):
             for r in range(rows):
                 kth = logits[t, r].topk(3).values[2 - (r + t) % 3]
-                logits[t, r, V - 1] = kth - 0.01 * ((r + t) % 2)
+                logits[t, r, V - 1] = kth - 0.01 * (1 + (r + t) % 2)  # never an exact tie
     elif kind == "all_finish":
         logits[3, :, V - 1] = 30.0
     elif kind == "eos_first":

@@ -1,10 +1,13 @@
 """Import the UNMODIFIED reference (ttanida/rgrg, /root/reference) in this container.
 
 TEST INFRASTRUCTURE ONLY.  /root/reference exists only in the build container, never on the
-GPU box, so nothing under `-m gpu`, smoke() or bench.py may import this file.  It is used
-  * by oracle/make_golden.py to generate the committed fixtures under tests/golden/, and
-  * by tests/test_oracle_vs_reference.py (skipped when /root/reference is absent)
-to pin oracle/rgrg_oracle.py (the CPU restatement) against the reference's own Python.
+GPU box.  This file is used
+  * by oracle/make_golden.py to generate the committed fixtures under tests/golden/ (from /root/reference), and
+  * by bench.py's CPU legs (`--impl reference`, `cpu_baseline`), which time the reference's own generate() on the host
+    cores from oracle/_ref/ — byte-for-byte copies of the eight hot-path files made by oracle/install_ref.py
+    (git-ignored, shipped to the GPU box like a built .so); when oracle/_ref/ is absent the CPU legs fall back to
+    the oracle port and say so (`kind: "port"`).
+The `-m gpu` tests and smoke() never import it.
 
 Two stubs + two patches; no reference file is edited or copied:
   1. sys.modules['torchinfo']                         (language_model.py:6  `from torchinfo import summary`)
@@ -17,7 +20,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("RGRG_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_VENDORED = os.path.join(_HERE, "_ref")  # unmodified copies made by oracle/install_ref.py (git-ignored; travels to the GPU box)
+
+
+def _default_root():
+    env = os.environ.get("RGRG_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/src/full_model"):
+        return "/root/reference"
+    return _VENDORED
+
+
+REFERENCE_ROOT = _default_root()
 
 
 def reference_available() -> bool:

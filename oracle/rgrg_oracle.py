@@ -453,9 +453,12 @@ def greedy_search(sd: SD, feats: torch.Tensor, max_length: Optional[int], record
 
 
 def beam_search(sd: SD, feats: torch.Tensor, max_length: int, num_beams: int, early_stopping: bool,
-                given_logits: Optional[torch.Tensor] = None) -> torch.Tensor:
+                given_logits: Optional[torch.Tensor] = None, stable_ties: bool = False) -> torch.Tensor:
     """language_model.py:529-607 with BeamSearchScorer(length_penalty=1.0, num_beam_hyps_to_keep=1) (:457-464).
-    given_logits [steps, rows * beams, V] replaces the model forward (bookkeeping tests)."""
+    given_logits [steps, rows * beams, V] replaces the model forward (bookkeeping tests).
+    stable_ties: order exactly tied candidates by lowest flat index (a stable descending sort).  torch.topk leaves the
+    order of equal elements unspecified (it differs between the CPU and CUDA kernels), so the reference's behaviour on
+    exact ties is implementation-defined; the engine's top-k breaks ties by lowest flat index."""
     from beam_scorer import BeamSearchScorer
 
     batch = feats.shape[0]
@@ -479,7 +482,11 @@ def beam_search(sd: SD, feats: torch.Tensor, max_length: int, num_beams: int, ea
             step_logits = logits[:, -1, :]
         scores = F.log_softmax(step_logits, dim=-1) + beam_scores[:, None]
         V = scores.shape[-1]
-        scores, tokens = torch.topk(scores.view(batch, num_beams * V), 2 * num_beams, dim=1, largest=True, sorted=True)
+        if stable_ties:
+            srt, order = torch.sort(scores.view(batch, num_beams * V), dim=1, descending=True, stable=True)
+            scores, tokens = srt[:, : 2 * num_beams], order[:, : 2 * num_beams]
+        else:
+            scores, tokens = torch.topk(scores.view(batch, num_beams * V), 2 * num_beams, dim=1, largest=True, sorted=True)
         indices = torch.div(tokens, V, rounding_mode="floor")
         tokens = tokens % V
         out = scorer.process(ids, scores, tokens, indices, pad_token_id=PAD, eos_token_id=EOS)

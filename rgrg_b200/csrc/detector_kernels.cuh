@@ -61,11 +61,70 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ img
   }
 }
 
+// 8 consecutive channels of an activation row, bf16 (fast path) or fp32 (detector_precise parity path)
+__device__ __forceinline__ void load8(const bf16* p, float* f) { unpack8(*reinterpret_cast<const uint4*>(p), f); }
+__device__ __forceinline__ void load8(const float* p, float* f) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store8(bf16* p, const float* f) { *reinterpret_cast<uint4*>(p) = pack8(f); }
+__device__ __forceinline__ void store8(float* p, const float* f) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+// fp32 stem for the parity path: conv1 7x7 s2 p3 + folded BN + ReLU (one thread per output element), then maxpool 3x3 s2 p1
+__global__ void stem_conv_f32_kernel(const float* __restrict__ img, const float* __restrict__ w /*[49][64]*/,
+                                     const float* __restrict__ bias, float* __restrict__ out /*[B,S/2,S/2,64]*/, int B, int S) {
+  const int C2 = S / 2;
+  const size_t total = static_cast<size_t>(B) * C2 * C2 * 64;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i & 63);
+    size_t t = i >> 6;
+    const int x = static_cast<int>(t % C2);
+    t /= C2;
+    const int y = static_cast<int>(t % C2);
+    const int b = static_cast<int>(t / C2);
+    const float* src = img + static_cast<size_t>(b) * S * S;
+    float acc = 0.0f;
+    for (int ky = 0; ky < 7; ++ky) {
+      const int iy = 2 * y - 3 + ky;
+      if (iy < 0 || iy >= S) continue;
+      for (int kx = 0; kx < 7; ++kx) {
+        const int ix = 2 * x - 3 + kx;
+        if (ix < 0 || ix >= S) continue;
+        acc = fmaf(src[static_cast<size_t>(iy) * S + ix], w[(ky * 7 + kx) * 64 + c], acc);
+      }
+    }
+    out[i] = fmaxf(acc + bias[c], 0.0f);
+  }
+}
+__global__ void maxpool3x3s2_f32_kernel(const float* __restrict__ in /*[B,H,H,64]*/, float* __restrict__ out /*[B,H/2,H/2,64]*/, int B, int H) {
+  const int P = H / 2;
+  const size_t total = static_cast<size_t>(B) * P * P * 64;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i & 63);
+    size_t t = i >> 6;
+    const int x = static_cast<int>(t % P);
+    t /= P;
+    const int y = static_cast<int>(t % P);
+    const int b = static_cast<int>(t / P);
+    float m = -INFINITY;
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int yy = 2 * y + dy, xx = 2 * x + dx;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < H) m = fmaxf(m, in[((static_cast<size_t>(b) * H + yy) * H + xx) * 64 + c]);
+      }
+    out[i] = m;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // im2col for 3x3 / pad 1 convolutions (stride 1 or 2), NHWC bf16 -> [B*Ho*Wo, 9*C] with K index (tap, c).
 // Used for the three stride-2 3x3 convs of ResNet-50 v1.5 (and as the bring-up path of the stride-1 ones).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void im2col3x3_kernel(const bf16* __restrict__ in, bf16* __restrict__ col, int B, int H, int W, int C,
+template <class TAct>
+__global__ void im2col3x3_kernel(const TAct* __restrict__ in, TAct* __restrict__ col, int B, int H, int W, int C,
                                  int stride, int Ho, int Wo) {
   const int cv = C / 8;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * 9 * cv;
@@ -80,15 +139,15 @@ __global__ void im2col3x3_kernel(const bf16* __restrict__ in, bf16* __restrict__
     const int ho = static_cast<int>(t % Ho);
     const int b = static_cast<int>(t / Ho);
     const int y = ho * stride + tap / 3 - 1, x = wo * stride + tap % 3 - 1;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (y >= 0 && y < H && x >= 0 && x < W)
-      v = *reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(b) * H + y) * W + x) * C + c8 * 8);
-    *reinterpret_cast<uint4*>(col + i * 8) = v;
+    float v[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    if (y >= 0 && y < H && x >= 0 && x < W) load8(in + ((static_cast<size_t>(b) * H + y) * W + x) * C + c8 * 8, v);
+    store8(col + i * 8, v);
   }
 }
 
 // 1x1 stride-2 sampling (downsample branch of the first block of layers 2-4): out[b,ho,wo,:] = in[b,2ho,2wo,:]
-__global__ void subsample2_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C) {
+template <class TAct>
+__global__ void subsample2_kernel(const TAct* __restrict__ in, TAct* __restrict__ out, int B, int H, int W, int C) {
   const int cv = C / 8, Ho = H / 2, Wo = W / 2;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * cv;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -99,8 +158,9 @@ __global__ void subsample2_kernel(const bf16* __restrict__ in, bf16* __restrict_
     t /= Wo;
     const int ho = static_cast<int>(t % Ho);
     const int b = static_cast<int>(t / Ho);
-    *reinterpret_cast<uint4*>(out + i * 8) =
-        *reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(b) * H + 2 * ho) * W + 2 * wo) * C + c8 * 8);
+    float v[8];
+    load8(in + ((static_cast<size_t>(b) * H + 2 * ho) * W + 2 * wo) * C + c8 * 8, v);
+    store8(out + i * 8, v);
   }
 }
 
@@ -413,9 +473,10 @@ __device__ __forceinline__ void axis_taps(float start, float bin, int p, int siz
   }
 }
 
-__global__ void __launch_bounds__(256) roi_align_kernel(const bf16* __restrict__ feats, const float* __restrict__ boxes /*[B,1000,4]*/,
+template <class TAct>
+__global__ void __launch_bounds__(256) roi_align_kernel(const TAct* __restrict__ feats, const float* __restrict__ boxes /*[B,1000,4]*/,
                                                         const int* __restrict__ count, const int* __restrict__ offsets,
-                                                        bf16* __restrict__ out, int f, int C, float scale) {
+                                                        TAct* __restrict__ out, int f, int C, float scale) {
   const int b = blockIdx.y, j = blockIdx.x;
   if (j >= count[b]) return;
   __shared__ AxisTaps s_y[8], s_x[8];
@@ -427,8 +488,8 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const bf16* __restrict__
     else axis_taps(x1, rw / 8.0f, threadIdx.x - 8, f, s_x[threadIdx.x - 8]);
   }
   __syncthreads();
-  const bf16* fm = feats + static_cast<size_t>(b) * f * f * C;
-  bf16* dst = out + static_cast<size_t>(offsets[b] + j) * 64 * C;
+  const TAct* fm = feats + static_cast<size_t>(b) * f * f * C;
+  TAct* dst = out + static_cast<size_t>(offsets[b] + j) * 64 * C;
   for (int c0 = threadIdx.x * 8; c0 < C; c0 += 256 * 8) {
     for (int bin = 0; bin < 64; ++bin) {
       const AxisTaps& ty = s_y[bin >> 3];
@@ -439,16 +500,15 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const bf16* __restrict__
       for (int iy = 0; iy < ty.n; ++iy) {
         for (int ix = 0; ix < tx.n; ++ix) {
           const float w = ty.w[iy] * tx.w[ix];
-          const uint4 v = *reinterpret_cast<const uint4*>(fm + (static_cast<size_t>(ty.idx[iy]) * f + tx.idx[ix]) * C + c0);
           float fv[8];
-          unpack8(v, fv);
+          load8(fm + (static_cast<size_t>(ty.idx[iy]) * f + tx.idx[ix]) * C + c0, fv);
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, fv[e], acc[e]);
         }
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] *= 0.25f;
-      *reinterpret_cast<uint4*>(dst + static_cast<size_t>(bin) * C + c0) = pack8(acc);
+      store8(dst + static_cast<size_t>(bin) * C + c0, acc);
     }
   }
 }
@@ -544,7 +604,8 @@ __global__ void __launch_bounds__(256) roi_tail_kernel(const float* __restrict__
 // RoIAlign is linear, so mean over the 8x8 bins == weighted sum over feature cells with separable weights
 // WY[row] * WX[col] (each axis: 16 sample points x 2 taps / 16).  fp32 output [B*29, C].
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) roi_mean_kernel(const bf16* __restrict__ feats, const float* __restrict__ boxes,
+template <class TAct>
+__global__ void __launch_bounds__(256) roi_mean_kernel(const TAct* __restrict__ feats, const float* __restrict__ boxes,
                                                        const int* __restrict__ count, const int* __restrict__ top_idx,
                                                        float* __restrict__ out, int f, int C, float scale) {
   const int c = blockIdx.x, b = blockIdx.y;
@@ -571,7 +632,7 @@ __global__ void __launch_bounds__(256) roi_mean_kernel(const bf16* __restrict__ 
     (axis == 0 ? s_wy : s_wx)[cell] = w * (1.0f / 16.0f);
   }
   __syncthreads();
-  const bf16* fm = feats + static_cast<size_t>(b) * f * f * C;
+  const TAct* fm = feats + static_cast<size_t>(b) * f * f * C;
   for (int c0 = threadIdx.x * 8; c0 < C; c0 += 256 * 8) {
     float acc[8];
 #pragma unroll
@@ -583,7 +644,7 @@ __global__ void __launch_bounds__(256) roi_mean_kernel(const bf16* __restrict__ 
         const float w = wy * s_wx[x];
         if (w == 0.0f) continue;
         float fv[8];
-        unpack8(*reinterpret_cast<const uint4*>(fm + (static_cast<size_t>(y) * f + x) * C + c0), fv);
+        load8(fm + (static_cast<size_t>(y) * f + x) * C + c0, fv);
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = fmaf(w, fv[e], acc[e]);
       }
@@ -677,6 +738,16 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict_
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     out[i] = f2bf(in[i]);
+}
+// out[i] = bias[i % N] + sum_s parts[s][i]   (test harness of the split-K GEMM form)
+__global__ void sum_parts_kernel(const float* __restrict__ parts, int nparts, long long total, const float* __restrict__ bias, int N,
+                                 float* __restrict__ out) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v = bias ? bias[i % N] : 0.0f;
+    for (int s = 0; s < nparts; ++s) v += parts[s * total + i];
+    out[i] = v;
+  }
 }
 // folded BN: scale = gamma / sqrt(var + eps), bias = beta - mean * scale
 __global__ void bn_fold_kernel(const float* g, const float* b, const float* mean, const float* var, float* scale, float* bias,

@@ -70,6 +70,7 @@ struct Linear {
   float* bias = nullptr;
   int N = 0, K = 0;
   CUtensorMap tm[4];  // TMA maps for N-tile widths 64 / 128 / 192 / 256
+  float* w32 = nullptr;  // fp32 twin [N, K] (detector_precise parity mode only)
   void make_maps() {
     for (int i = 0; i < 4; ++i) tm[i] = tc::make_tmap_2d(w, N, K, 64 * (i + 1));
   }
@@ -170,6 +171,7 @@ struct rgrg_engine {
   std::string err;
   int64_t launches = 0;
   bool weights_ready = false;
+  bool precise_weights = false;  // fp32 twins of the detector weights were built (detector_precise was set before finalize)
   int opt_implicit_conv = 1;
   int opt_cuda_graph = 1;
   int opt_gemm_impl = 0;
@@ -226,7 +228,7 @@ struct rgrg_engine {
                      &prop_scores, &prop_count, &roi_off, &pooled, &f6, &f7, &pred_out, &detected, &top_idx,
                      &top_scores, &top_boxes, &mean2048, &trf, &s0, &s1, &sel_logits, &selected, &sel_rows, &num_sel,
                      &lm_in, &kv_cache, &h, &x, &q, &attn_o, &mlp_mid, &a1, &img, &part_val, &part_idx, &ids,
-                     &unfinished, &unf_count, &step, &logits_tmp, &splitk_parts, &b_ids2, &b_anc[0], &b_anc[1], &b_scores, &b_cand_score,
+                     &unfinished, &unf_count, &step, &logits_tmp, &splitk_parts, &p_act[0], &p_act[1], &p_t1, &p_t2, &p_idb, &p_sub, &p_col, &p_c1, &p_feats, &p_rpn_t, &p_pooled, &p_f6, &p_f7, &b_ids2, &b_anc[0], &b_anc[1], &b_scores, &b_cand_score,
                      &b_cand_token, &b_cand_beam, &b_hyp_score, &b_hyp_len, &b_hyp_tok, &b_hyp_count, &b_worst, &b_done, &b_not_done};
     for (DevBuf* b : all) b->release();
   }
@@ -382,7 +384,7 @@ struct rgrg_engine {
     const int Ho = H / stride, Wo = Wd / stride;
     const size_t total = static_cast<size_t>(B) * Ho * Wo * 9 * (C / 8);
     const int grid = static_cast<int>(std::min<size_t>(ceil_div64(total, 256), 148 * 16));
-    det::im2col3x3_kernel<<<grid, 256, 0, st>>>(in, colbuf, B, H, Wd, C, stride, Ho, Wo);
+    det::im2col3x3_kernel<bf16><<<grid, 256, 0, st>>>(in, colbuf, B, H, Wd, C, stride, Ho, Wo);
     KERNEL_CHECK();
     ++launches;
   }
@@ -465,6 +467,11 @@ struct rgrg_engine {
     }
     det::repack_oihw_kernel<bf16><<<grid_for(static_cast<long long>(L.N) * L.K), 256>>>(dw, L.w, scale, L.N, cin, R);
     KERNEL_CHECK();
+    if (opt_detector_precise) {
+      L.w32 = walloc<float>(static_cast<size_t>(L.N) * L.K);
+      det::repack_oihw_kernel<float><<<grid_for(static_cast<long long>(L.N) * L.K), 256>>>(dw, L.w32, scale, L.N, cin, R);
+      KERNEL_CHECK();
+    }
     CUDA_CHECK(cudaDeviceSynchronize());
     free_tmps();
     L.make_maps();
@@ -488,13 +495,14 @@ struct rgrg_engine {
   }
 
   // nn.Linear weight [N, K] (already K-major) -> bf16 rows [row0, row0+N) of dst
-  void put_linear_rows(const std::string& name, bf16* dst_w, float* dst_b, int row0, int K) {
+  void put_linear_rows(const std::string& name, bf16* dst_w, float* dst_b, int row0, int K, float* dst_w32 = nullptr) {
     const HostRef& w = need(name + ".weight");
     const int N = static_cast<int>(w.shape[0]);
     if (w.numel() != static_cast<int64_t>(N) * K) throw std::runtime_error("bad shape for " + name);
     const float* dw = upload(w, stage);
     det::cast_bf16_kernel<<<grid_for(w.numel()), 256>>>(dw, dst_w + static_cast<size_t>(row0) * K, w.numel());
     KERNEL_CHECK();
+    if (dst_w32) CUDA_CHECK(cudaMemcpy(dst_w32 + static_cast<size_t>(row0) * K, dw, static_cast<size_t>(w.numel()) * 4, cudaMemcpyDeviceToDevice));
     CUDA_CHECK(cudaMemcpy(dst_b + row0, need(name + ".bias").p, N * 4, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaDeviceSynchronize());
   }
@@ -505,7 +513,8 @@ struct rgrg_engine {
     L.K = static_cast<int>(w.numel() / w.shape[0]);
     L.w = walloc<bf16>(static_cast<size_t>(L.N) * L.K);
     L.bias = walloc<float>(L.N);
-    put_linear_rows(name, L.w, L.bias, 0, L.K);
+    if (opt_detector_precise && name.find("object_detector") == 0) L.w32 = walloc<float>(static_cast<size_t>(L.N) * L.K);
+    put_linear_rows(name, L.w, L.bias, 0, L.K, L.w32);
     L.make_maps();
     return L;
   }
@@ -586,8 +595,9 @@ struct rgrg_engine {
       rpn_heads.K = 2048;
       rpn_heads.w = walloc<bf16>(800 * 2048);
       rpn_heads.bias = walloc<float>(800);
-      put_linear_rows(rp + ".cls_logits", rpn_heads.w, rpn_heads.bias, 0, 2048);
-      put_linear_rows(rp + ".bbox_pred", rpn_heads.w, rpn_heads.bias, 160, 2048);
+      if (opt_detector_precise) rpn_heads.w32 = walloc<float>(800 * 2048);
+      put_linear_rows(rp + ".cls_logits", rpn_heads.w, rpn_heads.bias, 0, 2048, rpn_heads.w32);
+      put_linear_rows(rp + ".bbox_pred", rpn_heads.w, rpn_heads.bias, 160, 2048, rpn_heads.w32);
       rpn_heads.make_maps();
     }
     // ---- RoI heads: fc6 input is flattened (c, ph, pw) in the reference; our RoIAlign emits (bin, c)
@@ -602,6 +612,11 @@ struct rgrg_engine {
       const float* dw = upload(w, stage);
       det::repack_oihw_kernel<bf16><<<grid_for(w.numel()), 256>>>(dw, fc6.w, nullptr, fc6.N, 2048, 64);
       KERNEL_CHECK();
+      if (opt_detector_precise) {
+        fc6.w32 = walloc<float>(static_cast<size_t>(fc6.N) * fc6.K);
+        det::repack_oihw_kernel<float><<<grid_for(w.numel()), 256>>>(dw, fc6.w32, nullptr, fc6.N, 2048, 64);
+        KERNEL_CHECK();
+      }
       CUDA_CHECK(cudaDeviceSynchronize());
       fc6.make_maps();
     }
@@ -611,8 +626,9 @@ struct rgrg_engine {
       pred.K = 1024;
       pred.w = walloc<bf16>(150 * 1024);
       pred.bias = walloc<float>(150);
-      put_linear_rows(rh + ".box_predictor.cls_score", pred.w, pred.bias, 0, 1024);
-      put_linear_rows(rh + ".box_predictor.bbox_pred", pred.w, pred.bias, 30, 1024);
+      if (opt_detector_precise) pred.w32 = walloc<float>(150 * 1024);
+      put_linear_rows(rh + ".box_predictor.cls_score", pred.w, pred.bias, 0, 1024, pred.w32);
+      put_linear_rows(rh + ".box_predictor.bbox_pred", pred.w, pred.bias, 30, 1024, pred.w32);
       pred.make_maps();
     }
     dimred = make_linear_f32(rh + ".dim_reduction");
@@ -682,6 +698,7 @@ struct rgrg_engine {
     CUDA_CHECK(cudaFuncSetAttribute(det::rpn_proposals_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(det::RPN_SMEM)));
     weights_ready = true;
+    precise_weights = opt_detector_precise != 0;
   }
 
   // ================================================================================================================
@@ -761,7 +778,7 @@ struct rgrg_engine {
         if (bw.stride == 2) {
           ProfScope ps(this, "subsample", st);
           const size_t total = static_cast<size_t>(M_out) * (bw.cin / 8);
-          det::subsample2_kernel<<<static_cast<int>(std::min<size_t>(ceil_div64(total, 256), 148 * 16)), 256, 0, st>>>(
+          det::subsample2_kernel<bf16><<<static_cast<int>(std::min<size_t>(ceil_div64(total, 256), 148 * 16)), 256, 0, st>>>(
               xin, sub.as<bf16>(), B, H, H, bw.cin);
           KERNEL_CHECK();
           ++launches;
@@ -784,14 +801,88 @@ struct rgrg_engine {
     ++launches;
   }
 
+  // ---- fp32 parity path of the detector ("detector_precise"): the same layer sequence with fp32 operands, fp32 NHWC
+  // activations and fp32 accumulation on CUDA cores, so that the decision tensors (objectness, deltas, class logits) carry
+  // reference-grade arithmetic and the per-class top-1 region INDICES can be compared with the oracle (SURVEY.md §7/§8(d):
+  // the bf16 tensor-core path flips arg-maxes that are decided below bf16 resolution).  Not a product path: ~100x slower.
+  DevBuf p_act[2], p_t1, p_t2, p_idb, p_sub, p_col, p_c1, p_feats, p_rpn_t, p_pooled, p_f6, p_f7;
+  template <int ACT, int RES>
+  void gemm_f32(const float* A, int M, const Linear& W, float* out, const float* res, cudaStream_t st) {
+    if (!W.w32) throw std::runtime_error("detector_precise must be set before the weights are finalized");
+    simt::launch<float, float, EpiStoreT<false, ACT, RES, true>>(A, W.w32, M, W.N, W.K, epi<false, ACT, RES, true>(out, W.bias, W.N, res), st);
+    ++launches;
+  }
+  const float* conv3x3_f32_cols(const float* in, int B, int H, int C, int stride, cudaStream_t st) {
+    const int Ho = H / stride;
+    p_col.ensure(static_cast<size_t>(B) * Ho * Ho * 9 * C * 4);
+    const size_t total = static_cast<size_t>(B) * Ho * Ho * 9 * (C / 8);
+    det::im2col3x3_kernel<float><<<static_cast<int>(std::min<size_t>(ceil_div64(total, 256), 148 * 16)), 256, 0, st>>>(
+        in, p_col.as<float>(), B, H, H, C, stride, Ho, Ho);
+    KERNEL_CHECK();
+    ++launches;
+    return p_col.as<float>();
+  }
+  void run_backbone_rpn_precise(const float* img_dev, int B, int S, cudaStream_t st) {
+    const int P = S / 4, f = S / 32;
+    const size_t big = static_cast<size_t>(B) * P * P * 256 * 4;
+    p_c1.ensure(static_cast<size_t>(B) * (S / 2) * (S / 2) * 64 * 4);
+    p_act[0].ensure(big);
+    p_act[1].ensure(big);
+    p_t1.ensure(big / 2);
+    p_t2.ensure(big / 4);
+    p_idb.ensure(big);
+    p_sub.ensure(big / 4);
+    p_feats.ensure(static_cast<size_t>(B) * f * f * 2048 * 4);
+    p_rpn_t.ensure(static_cast<size_t>(B) * f * f * 2048 * 4);
+    det::stem_conv_f32_kernel<<<148 * 8, 256, 0, st>>>(img_dev, stem_w, stem_b, p_c1.as<float>(), B, S);
+    det::maxpool3x3s2_f32_kernel<<<148 * 8, 256, 0, st>>>(p_c1.as<float>(), p_act[0].as<float>(), B, S / 2);
+    KERNEL_CHECK();
+    launches += 2;
+    int cur = 0, H = P;
+    for (size_t i = 0; i < blocks.size(); ++i) {
+      const BlockW& bw = blocks[i];
+      const float* xin = p_act[cur].as<float>();
+      float* yout = (i + 1 == blocks.size()) ? p_feats.as<float>() : p_act[cur ^ 1].as<float>();
+      const int Ho = H / bw.stride;
+      const int M_in = B * H * H, M_out = B * Ho * Ho;
+      gemm_f32<ACT_RELU, RES_NONE>(xin, M_in, bw.c1, p_t1.as<float>(), nullptr, st);
+      gemm_f32<ACT_RELU, RES_NONE>(conv3x3_f32_cols(p_t1.as<float>(), B, H, bw.width, bw.stride, st), M_out, bw.c2, p_t2.as<float>(), nullptr, st);
+      const float* identity = xin;
+      if (bw.has_ds) {
+        const float* ds_in = xin;
+        if (bw.stride == 2) {
+          const size_t total = static_cast<size_t>(M_out) * (bw.cin / 8);
+          det::subsample2_kernel<float><<<static_cast<int>(std::min<size_t>(ceil_div64(total, 256), 148 * 16)), 256, 0, st>>>(
+              xin, p_sub.as<float>(), B, H, H, bw.cin);
+          KERNEL_CHECK();
+          ++launches;
+          ds_in = p_sub.as<float>();
+        }
+        gemm_f32<ACT_NONE, RES_NONE>(ds_in, M_out, bw.ds, p_idb.as<float>(), nullptr, st);
+        identity = p_idb.as<float>();
+      }
+      gemm_f32<ACT_RELU, RES_F32>(p_t2.as<float>(), M_out, bw.c3, yout, identity, st);
+      cur ^= 1;
+      H = Ho;
+    }
+    gemm_f32<ACT_RELU, RES_NONE>(conv3x3_f32_cols(p_feats.as<float>(), B, f, 2048, 1, st), B * f * f, rpn_conv, p_rpn_t.as<float>(), nullptr, st);
+    gemm_f32<ACT_NONE, RES_NONE>(p_rpn_t.as<float>(), B * f * f, rpn_heads, rpn_out.as<float>(), nullptr, st);
+  }
+
   // full detector + selection; leaves lm_in [R,1024] bf16 on the device; returns R
   int run_detect(const float* img_dev, int B, int S, cudaStream_t st) {
     ensure_detector_ws(B, S);
     const int f = S / 32;
-    run_backbone(img_dev, B, S, feats.as<bf16>(), st);
-    // RPN head: 3x3 conv + ReLU, then both 1x1 heads as one N = 160 + 640 GEMM with fp32 (decision-critical) output
-    conv3x3("rpn_conv", feats.as<bf16>(), B, f, f, 2048, 1, rpn_conv, epi<true, ACT_RELU, RES_NONE, true>(rpn_t.p, rpn_conv.bias, 2048), st);
-    gemm("rpn_heads", rpn_t.as<bf16>(), B * f * f, rpn_heads, epi<false, ACT_NONE, RES_NONE, true>(rpn_out.p, rpn_heads.bias, 800), st, false);
+    const bool precise = opt_detector_precise != 0;
+    if (precise && !precise_weights) throw std::runtime_error("detector_precise must be set before the weights are finalized");
+    if (precise) {
+      run_backbone_rpn_precise(img_dev, B, S, st);
+    } else {
+      run_backbone(img_dev, B, S, feats.as<bf16>(), st);
+      // RPN head: 3x3 conv + ReLU, then both 1x1 heads as one N = 160 + 640 GEMM with fp32 (decision-critical) output
+      conv3x3("rpn_conv", feats.as<bf16>(), B, f, f, 2048, 1, rpn_conv, epi<true, ACT_RELU, RES_NONE, true>(rpn_t.p, rpn_conv.bias, 2048), st);
+      gemm("rpn_heads", rpn_t.as<bf16>(), B * f * f, rpn_heads, epi<false, ACT_NONE, RES_NONE, true>(rpn_out.p, rpn_heads.bias, 800), st, false);
+    }
     det::RpnIn in{};
     in.obj = rpn_out.as<float>();
     in.deltas = rpn_out.as<float>() + 160;
@@ -809,31 +900,52 @@ struct rgrg_engine {
     CUDA_CHECK(cudaMemcpyAsync(&P_total, roi_off.as<int>() + B, 4, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));  // the RoI GEMMs are sized by the number of surviving proposals
     last_P = P_total;
-    ensure_roi_ws(P_total);
+    const size_t prow = static_cast<size_t>(std::max(P_total, 1));
     const float scale = exp2f(roundf(log2f(static_cast<float>(f) / static_cast<float>(S))));  // poolers.py _infer_scale
-    if (P_total > 0) {
-      {
-        ProfScope ps(this, "roi_align", st);
-        det::roi_align_kernel<<<dim3(TOPK, B), 256, 0, st>>>(feats.as<bf16>(), prop_boxes.as<float>(), prop_count.as<int>(),
-                                                            roi_off.as<int>(), pooled.as<bf16>(), f, 2048, scale);
+    if (precise) {
+      p_pooled.ensure(prow * 131072 * 4);
+      p_f6.ensure(prow * 1024 * 4);
+      p_f7.ensure(prow * 1024 * 4);
+      pred_out.ensure(prow * 150 * 4);
+      if (P_total > 0) {
+        det::roi_align_kernel<float><<<dim3(TOPK, B), 256, 0, st>>>(p_feats.as<float>(), prop_boxes.as<float>(), prop_count.as<int>(),
+                                                                    roi_off.as<int>(), p_pooled.as<float>(), f, 2048, scale);
         KERNEL_CHECK();
         ++launches;
+        gemm_f32<ACT_RELU, RES_NONE>(p_pooled.as<float>(), P_total, fc6, p_f6.as<float>(), nullptr, st);
+        gemm_f32<ACT_RELU, RES_NONE>(p_f6.as<float>(), P_total, fc7, p_f7.as<float>(), nullptr, st);
+        gemm_f32<ACT_NONE, RES_NONE>(p_f7.as<float>(), P_total, pred, pred_out.as<float>(), nullptr, st);
       }
-      gemm("fc6", pooled.as<bf16>(), P_total, fc6, epi<true, ACT_RELU, RES_NONE, true>(f6.p, fc6.bias, 1024), st, false);
-      gemm("fc7", f6.as<bf16>(), P_total, fc7, epi<true, ACT_RELU, RES_NONE, true>(f7.p, fc7.bias, 1024), st, true);
-      gemm("box_predictor", f7.as<bf16>(), P_total, pred, epi<false, ACT_NONE, RES_NONE, true>(pred_out.p, pred.bias, 150), st, true);
+    } else {
+      ensure_roi_ws(P_total);
+      if (P_total > 0) {
+        {
+          ProfScope ps(this, "roi_align", st);
+          det::roi_align_kernel<bf16><<<dim3(TOPK, B), 256, 0, st>>>(feats.as<bf16>(), prop_boxes.as<float>(), prop_count.as<int>(),
+                                                                     roi_off.as<int>(), pooled.as<bf16>(), f, 2048, scale);
+          KERNEL_CHECK();
+          ++launches;
+        }
+        gemm("fc6", pooled.as<bf16>(), P_total, fc6, epi<true, ACT_RELU, RES_NONE, true>(f6.p, fc6.bias, 1024), st, false);
+        gemm("fc7", f6.as<bf16>(), P_total, fc7, epi<true, ACT_RELU, RES_NONE, true>(f7.p, fc7.bias, 1024), st, true);
+        gemm("box_predictor", f7.as<bf16>(), P_total, pred, epi<false, ACT_NONE, RES_NONE, true>(pred_out.p, pred.bias, 150), st, true);
+      }
     }
     ProfScope ps_tail(this, "region_tail", st);
     det::RoiTailOut to{detected.as<uint8_t>(), top_idx.as<int>(), top_scores.as<float>(), top_boxes.as<float>()};
     det::roi_tail_kernel<<<B, 256, 0, st>>>(pred_out.as<float>(), 150, pred_out.as<float>() + 30, 150, prop_boxes.as<float>(),
                                             prop_count.as<int>(), roi_off.as<int>(), to, S);
     KERNEL_CHECK();
-    det::roi_mean_kernel<<<dim3(NREG, B), 256, 0, st>>>(feats.as<bf16>(), prop_boxes.as<float>(), prop_count.as<int>(),
-                                                        top_idx.as<int>(), mean2048.as<float>(), f, 2048, scale);
+    if (precise)
+      det::roi_mean_kernel<float><<<dim3(NREG, B), 256, 0, st>>>(p_feats.as<float>(), prop_boxes.as<float>(), prop_count.as<int>(),
+                                                                 top_idx.as<int>(), mean2048.as<float>(), f, 2048, scale);
+    else
+      det::roi_mean_kernel<bf16><<<dim3(NREG, B), 256, 0, st>>>(feats.as<bf16>(), prop_boxes.as<float>(), prop_count.as<int>(),
+                                                                top_idx.as<int>(), mean2048.as<float>(), f, 2048, scale);
     KERNEL_CHECK();
     launches += 2;
     const int rows = B * NREG;
-    // dim_reduction + selection MLP in fp32 on CUDA cores (decision-critical, 0.01 % of the FLOPs)
+    // dim_reduction + selection MLP (+ abnormal MLP) in fp32 on CUDA cores (decision-critical, 0.01 % of the FLOPs)
     simt_f32(mean2048.as<float>(), dimred.w, rows, 1024, 2048,
              epi<false, ACT_NONE, RES_NONE, true>(trf.p, dimred.bias, 1024), st);
     simt_f32(trf.as<float>(), sel0.w, rows, 512, 1024, epi<false, ACT_RELU, RES_NONE, true>(s0.p, sel0.bias, 512), st);
@@ -1579,7 +1691,7 @@ int rgrg_bbox_features(rgrg_engine_t* e, const float* images, int images_on_host
     CUDA_CHECK(cudaMemcpyAsync(e->prop_count.p, cnt.data(), cnt.size() * 4, cudaMemcpyHostToDevice, st));
     CUDA_CHECK(cudaMemcpyAsync(e->top_idx.p, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, st));
     const float scale = exp2f(roundf(log2f(static_cast<float>(f) / static_cast<float>(S))));
-    det::roi_mean_kernel<<<dim3(NREG, B), 256, 0, st>>>(e->feats.as<bf16>(), e->prop_boxes.as<float>(), e->prop_count.as<int>(),
+    det::roi_mean_kernel<bf16><<<dim3(NREG, B), 256, 0, st>>>(e->feats.as<bf16>(), e->prop_boxes.as<float>(), e->prop_count.as<int>(),
                                                         e->top_idx.as<int>(), e->mean2048.as<float>(), f, 2048, scale);
     KERNEL_CHECK();
     const int rows = B * NREG;
@@ -1682,7 +1794,7 @@ int rgrg_roi_align(rgrg_engine_t* e, const void* feats_bf16_dev, const float* bo
     e->roi_off.ensure(static_cast<size_t>(B + 1) * 4);
     det::roi_offsets_kernel<<<1, 32, 0, st>>>(count_dev, e->roi_off.as<int>(), B);
     const float scale = exp2f(roundf(log2f(static_cast<float>(feat) / static_cast<float>(image_size))));
-    det::roi_align_kernel<<<dim3(TOPK, B), 256, 0, st>>>(static_cast<const bf16*>(feats_bf16_dev), boxes_dev, count_dev,
+    det::roi_align_kernel<bf16><<<dim3(TOPK, B), 256, 0, st>>>(static_cast<const bf16*>(feats_bf16_dev), boxes_dev, count_dev,
                                                         e->roi_off.as<int>(), static_cast<bf16*>(out_bf16_dev), feat, C, scale);
     KERNEL_CHECK();
     e->launches += 2;
@@ -1721,6 +1833,20 @@ int rgrg_gemm_bf16(rgrg_engine_t* e, const void* A_dev, const void* W_dev, const
     const bf16* A = static_cast<const bf16*>(A_dev);
     try {
       if (impl != 2) L.make_maps();
+      if (impl == 6) {  // the decoder's split-K form: 4 K slices -> fp32 partial sums, reduced (+ bias) afterwards
+        if (act != ACT_NONE) throw std::runtime_error("split-K test path has no activation");
+        DevBuf parts;
+        parts.ensure(static_cast<size_t>(4) * M * N * 4);
+        e->opt_gemm_impl = 0;
+        e->gemm_splitk("test_gemm", A, M, L, parts.as<float>(), 4, st);
+        const long long total = static_cast<long long>(M) * N;
+        det::sum_parts_kernel<<<rgrg_engine::grid_for(total), 256, 0, st>>>(parts.as<float>(), 4, total, bias_dev, N, out_dev);
+        KERNEL_CHECK();
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        parts.release();
+        e->opt_gemm_impl = saved;
+        return 0;
+      }
       if (bias_dev) {
         if (act == ACT_RELU) e->gemm("test_gemm", A, M, L, rgrg_engine::epi<false, ACT_RELU, RES_NONE, true>(out_dev, bias_dev, N), st, true, fbn);
         else if (act == ACT_GELU_NEW) e->gemm("test_gemm", A, M, L, rgrg_engine::epi<false, ACT_GELU_NEW, RES_NONE, true>(out_dev, bias_dev, N), st, true, fbn);
@@ -1844,6 +1970,29 @@ int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst, size_t b
     else if (n == "selection_logits") b = &e->sel_logits;
     else if (n == "region_features_2048") b = &e->mean2048;
     else if (n == "fc7") b = &e->f7;
+    else if (n.rfind("max_clusters_", 0) == 0) {  // tuning: co-resident clusters of the given size for a 216 KB-smem GEMM CTA
+      const int cs = atoi(n.c_str() + 13);
+      auto kern = tc::gemm_tc_kernel<256, 4, EpiStoreT<true, ACT_GELU_NEW, RES_NONE, true>, true>;
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemLayout<256, 4>::TOTAL);
+      cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cs * 16);
+      cfg.blockDim = dim3(tc::NUM_THREADS);
+      cfg.dynamicSmemBytes = tc::SmemLayout<256, 4>::TOTAL;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = cs;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int nc = 0;
+      const cudaError_t er = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+      cudaGetLastError();
+      if (bytes < 4) throw std::runtime_error("need 4 bytes");
+      *static_cast<int*>(host_dst) = er == cudaSuccess ? nc : -1;
+      return 0;
+    }
     else if (n == "cluster16_max_active") {
       if (bytes < 4) throw std::runtime_error("need 4 bytes");
       e->ln_head_available();

@@ -71,7 +71,11 @@ class Engine:
     def kernel_launches(self) -> int:
         return int(self._lib.rgrg_kernel_launches(self._h))
 
-    def load_state_dict(self, state_dict: Dict[str, torch.Tensor]):
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], detector_precise: bool = False):
+        """detector_precise: also keep fp32 twins of the detector weights and run the detector in fp32 on CUDA cores
+        (parity mode: region indices comparable with the fp32 reference; ~100x slower than the bf16 tensor-core path)."""
+        if detector_precise:
+            self.set_option("detector_precise", 1)
         keep = []
         for name, t in state_dict.items():
             if not torch.is_tensor(t) or not t.dtype.is_floating_point:

@@ -33,6 +33,33 @@ def test_gemm_matches_fp32_math(eng_bare, impl, M, N, K):
     assert err <= 2e-3 * max(1.0, ref.abs().max().item()), "max abs err %g" % err
 
 
+def test_gemm_fc6_shape_long_k(eng_bare):
+    """fc6 of the box head: K = 131 072 (2048 k-blocks), the longest reduction on the path."""
+    M, N, K = 64, 1024, 131072
+    A = _rand_bf16((M, K), 11)
+    W = _rand_bf16((N, K), 12, 0.003)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(13)).cuda()
+    ref = A.float() @ W.float().T + bias
+    for impl in (5, 4):
+        out = eng_bare.gemm(A, W, bias, act=0, impl=impl)
+        err = (out - ref).abs().max().item()
+        assert err <= 2e-3 * max(1.0, ref.abs().max().item()), "impl %d: max abs err %g" % (impl, err)
+    out = eng_bare.gemm(A, W, bias, act=1, impl=5)
+    assert (out - torch.relu(ref)).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K", [(928, 1024, 1024), (928, 1024, 4096), (37, 1024, 4096), (300, 512, 256)])
+def test_gemm_split_k_form(eng_bare, M, N, K):
+    """The decoder's residual projections: 4 K slices -> fp32 partial sums -> reduce (c_proj K = 1024, mlp c_proj K = 4096)."""
+    A = _rand_bf16((M, K), 21)
+    W = _rand_bf16((N, K), 22, 0.05)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(23)).cuda()
+    out = eng_bare.gemm(A, W, bias, act=0, impl=6)
+    ref = A.float() @ W.float().T + bias
+    err = (out - ref).abs().max().item()
+    assert err <= 2e-3 * max(1.0, ref.abs().max().item()), "max abs err %g" % err
+
+
 @pytest.mark.parametrize("act", [1, 2])
 def test_gemm_epilogue_activations(eng_bare, act):
     A = _rand_bf16((200, 128), 4)

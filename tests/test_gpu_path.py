@@ -48,20 +48,92 @@ def test_backbone_features_within_bf16_tolerance(model, images, oracle_detail):
     assert _rel(feats, oracle_detail["features"]) < 0.05  # 53 chained bf16 convs (~4 %)
 
 
-def test_detector_masks_and_regions(model, images, oracle_detail):
-    out = model._engine().detect(images.cuda())
+def _oracle_class_scores(synth_sd, oracle_detail, b, boxes):
+    """The oracle's 29 per-class scores (softmax over 30, background dropped) of arbitrary boxes of image b."""
+    with torch.no_grad():
+        pooled = O.box_roi_pool(oracle_detail["features"][b:b + 1], [boxes], 512)
+        _, cls, _ = O.box_head_and_predictor(synth_sd, pooled)
+    return torch.softmax(cls, -1)[:, 1:]
+
+
+def test_detector_masks_and_epsilon_optimal_regions(model, images, oracle_detail, synth_sd):
+    """bf16 tensor-core detector against the fp32 oracle.  Boolean outputs are exact.  Per-class top-1 proposals are decided
+    among ~900 overlapping proposals whose scores differ by less than bf16 resolution, so the index check
+    is the epsilon-optimal one: the proposal the engine picked for class c must score, UNDER THE ORACLE, within EPS of the
+    oracle's own best score for c (and the fp32 mode below pins the indices themselves)."""
+    EPS = 0.001  # the per-class scores live in [0.02, 0.06]; measured gap 2e-4
+    eng = model._engine()
+    out = eng.detect(images.cuda())
     det = oracle_detail["det"]
-    # boolean outputs: exact
     assert np.array_equal(out["detected"], det["class_detected"].numpy())
     assert np.array_equal(out["selected"], oracle_detail["selected"].numpy())
-    # proposals survive NMS in similar numbers
     ref_counts = np.array([p.shape[0] for p in oracle_detail["proposals"]])
-    assert np.all(np.abs(out["num_proposals"] - ref_counts) <= 0.1 * ref_counts)
-    # per-class top-1 proposal: epsilon-optimal under the oracle's own scores is not checkable across different
-    # proposal lists; the score itself must agree (flat across overlapping proposals)
-    assert np.abs(out["scores"] - det["top_scores"].numpy()).max() < 0.03
-    # region features feeding the decoder
-    assert _rel(torch.from_numpy(out["region_features"]), det["top_region_features"]) < 0.35
+    assert np.all(np.abs(out["num_proposals"] - ref_counts) <= 0.05 * ref_counts)
+    props = eng.debug_read("proposals", (2, 1000, 4))
+    worst = 0.0
+    for b in range(2):
+        chosen = torch.from_numpy(props[b][out["top_idx"][b]])  # [29, 4] the engine's pick per class
+        sc = _oracle_class_scores(synth_sd, oracle_detail, b, chosen)  # [29, 29]
+        own = sc[torch.arange(29), torch.arange(29)]
+        gap = (det["top_scores"][b] - own).max().item()
+        worst = max(worst, gap)
+        assert gap <= EPS, "image %d: engine's pick is %.5f below the oracle's best score" % (b, gap)
+        assert np.abs(out["scores"][b] - own.numpy()).max() < EPS  # the engine's own score of its pick
+    print("epsilon-optimality gap (bf16 detector): %.5f" % worst)
+    assert _rel(torch.from_numpy(out["region_features"]), det["top_region_features"]) < 0.35  # different (equally good) picks
+
+
+@pytest.fixture(scope="module")
+def precise_engine(synth_sd):
+    from rgrg_b200 import Engine
+
+    e = Engine(0)
+    e.load_state_dict(synth_sd, detector_precise=True)
+    yield e
+    e.close()
+
+
+def test_detector_fp32_mode_pins_region_indices(precise_engine, images, oracle_detail, synth_sd):
+    """`detector_precise`: fp32 operands / activations / accumulation.  Proposals, per-class top-1 proposal INDICES, boxes,
+    scores and region features equal the fp32 oracle's (the north-star's "bit-exact region indices" on identical
+    arithmetic precision); a pick may differ only where the oracle's own top-1 / top-2 margin is below fp32 noise."""
+    eng = precise_engine
+    out = eng.detect(images.cuda())
+    det = oracle_detail["det"]
+    assert np.array_equal(out["detected"], det["class_detected"].numpy())
+    assert np.array_equal(out["selected"], oracle_detail["selected"].numpy())
+    props = eng.debug_read("proposals", (2, 1000, 4))
+    mismatched = 0
+    for b in range(2):
+        ref_p = oracle_detail["proposals"][b]
+        n = int(out["num_proposals"][b])
+        assert n == ref_p.shape[0], "image %d: %d proposals vs %d" % (b, n, ref_p.shape[0])
+        # the same proposals (px); two proposals whose objectness differs by fp32 noise may swap places in the score order,
+        # so indices are compared through the box-to-box correspondence
+        d = (torch.from_numpy(props[b][:n])[:, None, :] - ref_p[None, :, :]).abs().amax(-1)  # [n, n]
+        dist, perm = d.min(1)
+        assert dist.max().item() < 2e-2 and len(set(perm.tolist())) == n
+        swapped = int((perm != torch.arange(n)).sum())
+        assert swapped <= 0.02 * n, "%d proposals out of order" % swapped
+        same = perm.numpy()[out["top_idx"][b]] == det_top_idx(oracle_detail, b)
+        mismatched += int((~same).sum())
+        if not same.all():
+            sc = _oracle_class_scores(synth_sd, oracle_detail, b, torch.from_numpy(props[b][out["top_idx"][b]]))
+            own = sc[torch.arange(29), torch.arange(29)]
+            assert ((det["top_scores"][b] - own)[torch.from_numpy(~same)] < 2e-6).all()  # only fp32-noise ties may differ
+        assert np.abs(out["boxes"][b][same] - det["top_region_boxes"][b].numpy()[same]).max() < 2e-2
+        assert np.abs(out["scores"][b][same] - det["top_scores"][b].numpy()[same]).max() < 1e-5
+        f_e, f_o = torch.from_numpy(out["region_features"][b][same]), det["top_region_features"][b][torch.from_numpy(same)]
+        assert _rel(f_e, f_o) < 1e-3
+    print("fp32 detector: %d of 58 per-class picks differ from the oracle" % mismatched)
+    assert mismatched <= 2
+
+
+def det_top_idx(oracle_detail, b):
+    roi = oracle_detail["roi"]
+    cls, reg = roi["class_logits"], roi["box_regression"]
+    out = O.top_regions(cls, reg, oracle_detail["proposals"], 512)
+    return out["top_idx"][b].numpy()
 
 
 def test_decoder_logits_teacher_forced(model, synth_sd, oracle_detail):
