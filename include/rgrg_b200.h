@@ -75,12 +75,15 @@ RGRG_API int rgrg_generate(rgrg_engine_t* e, const float* images, int images_on_
 RGRG_API int rgrg_lm_generate(rgrg_engine_t* e, const float* feats, int feats_on_host, int R, int max_length, int num_beams,
                      int early_stopping, int32_t* out_ids /* host [R, max_length] */, int* out_width, void* stream);
 
-/* replaces: ObjectDetector.forward(images) + BinaryClassifierRegionSelection.forward (inference branch).
+/* replaces: ObjectDetector.forward(images) + BinaryClassifierRegionSelection.forward (inference branch) and, when
+ * out_abnormal is given, BinaryClassifierRegionAbnormal.forward (binary_classifier_region_abnormal.py:31-57, the eval-mode
+ * extra of report_generation_model.py:103-106; `logit > -1`, NOT masked by class_detected — the reference masks later).
  * Host outputs as in rgrg_generate; out_region_features fp32 host [B,29,1024] (may be NULL);
- * out_top_idx int32 host [B,29] (may be NULL), out_num_proposals int32 host [B] (may be NULL). */
+ * out_top_idx int32 host [B,29] (may be NULL), out_num_proposals int32 host [B] (may be NULL),
+ * out_abnormal uint8 host [B,29] (may be NULL). */
 RGRG_API int rgrg_detect(rgrg_engine_t* e, const float* images, int images_on_host, int B, int S, uint8_t* out_selected,
                 uint8_t* out_detected, float* out_boxes, float* out_scores, float* out_region_features,
-                int32_t* out_top_idx, int32_t* out_num_proposals, int* out_R, void* stream);
+                int32_t* out_top_idx, int32_t* out_num_proposals, uint8_t* out_abnormal, int* out_R, void* stream);
 
 /* replaces: get_bbox_features(model, images, bbox_coordinates) (evaluate_bbox_variations.py:92-110): user boxes -> backbone ->
  * RoIAlign 8x8 -> AvgPool(8) -> dim_reduction.  boxes host fp32 [B,29,4] (x1,y1,x2,y2 in pixels);
@@ -94,6 +97,13 @@ RGRG_API int rgrg_bbox_features(rgrg_engine_t* e, const float* images, int image
  * (logits after consuming token t, language_model.py:258-399 with the cache of :169-170). */
 RGRG_API int rgrg_lm_forced_logits(rgrg_engine_t* e, const float* feats_dev, int R, const int32_t* forced_ids_dev,
                           int n_tokens, float* out_logits_dev, void* stream);
+
+/* Pre-processing in front of the path (replaces `get_image_tensor`, src/full_model/generate_reports_for_images.py:129-147:
+ * cv2 INTER_AREA resize to longest side 512 -> centre zero-pad to 512x512 -> (x/255 - 0.471)/0.302), bit-exact against
+ * cv2.resize + the albumentations 1.1.0 transforms.  image: uint8 grayscale [H, W] (host or device); out: fp32 [512*512]
+ * (host or device) = one image of the [B,1,512,512] batch rgrg_generate consumes.  Down-scaling only (max(H,W) >= 512). */
+RGRG_API int rgrg_preprocess(rgrg_engine_t* e, const uint8_t* image, int image_on_host, int H, int W, float* out, int out_on_host,
+                    void* stream);
 
 /* greedy-search bookkeeping only (language_model.py:629-650: arg-max, pad-if-finished, EOS tracking, stop rule) driven by
  * given logits: logits_steps dev fp32 [n_steps, R, 50257]; out_ids host int32 [R, max_length]; out_width = reference width.

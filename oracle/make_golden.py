@@ -47,6 +47,14 @@ def main():
     imgs = synth.synthetic_images(2, 512, seed=1001)
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
 
+    if only == "abnormal":
+        # ---- a9': abnormal classifier on the reference's own region features (binary_classifier_region_abnormal.py:31-57, eval)
+        g = np.load(os.path.join(OUT, "selection.npz"))
+        feats29, detected = torch.from_numpy(g["top_region_features"]), torch.from_numpy(g["class_detected"])
+        loss, pred = model.binary_classifier_region_abnormal(feats29, detected, torch.zeros_like(detected))
+        logits = model.binary_classifier_region_abnormal.classifier(feats29).squeeze(-1)
+        npz("abnormal.npz", predicted_abnormal_regions=pred, logits=logits)
+        return
     if only in ("lm_long", "lm_crafted"):
         lm_only(model, only)
         return

@@ -348,9 +348,10 @@ def region_selection(sd: SD, top_region_features: torch.Tensor, class_detected: 
 
 
 def region_abnormal(sd: SD, top_region_features: torch.Tensor, class_detected: torch.Tensor):
-    """binary_classifier_region_abnormal.py:31-57 — NOT on the generate() path."""
+    """binary_classifier_region_abnormal.py:31-57 — NOT on the generate() path.  Eval branch: returns
+    `logits > -1` for ALL 29 regions (:53-57: undetected regions are filtered later by the caller via class_detected)."""
     logits = _mlp3(sd, "binary_classifier_region_abnormal", top_region_features)
-    return (logits > -1) & class_detected, logits
+    return logits > -1, logits
 
 
 # ----------------------------------------------------------------------------------------------------------------------

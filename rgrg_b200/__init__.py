@@ -6,6 +6,7 @@ Nothing here falls back to PyTorch or the CPU: without the built library the eng
 """
 from . import _cabi  # noqa: F401
 from .engine import Engine  # noqa: F401
-from .model import LanguageModel, ReportGenerationModel, get_bbox_features  # noqa: F401
+from . import report_assembly  # noqa: F401
+from .model import LanguageModel, ReportGenerationModel, get_bbox_features, get_image_tensor  # noqa: F401
 
-__all__ = ["Engine", "ReportGenerationModel", "LanguageModel", "get_bbox_features"]
+__all__ = ["Engine", "ReportGenerationModel", "LanguageModel", "get_bbox_features", "get_image_tensor", "report_assembly"]

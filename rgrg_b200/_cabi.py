@@ -20,9 +20,10 @@ _PROTOTYPES = {
     "rgrg_finalize_weights": (_i, [c_p]),
     "rgrg_generate": (_i, [c_p, c_p, _i, _i, _i, _i, _i, _i, c_p, C.POINTER(_i), c_p, c_p, c_p, c_p, C.POINTER(_i), c_p]),
     "rgrg_lm_generate": (_i, [c_p, c_p, _i, _i, _i, _i, _i, c_p, C.POINTER(_i), c_p]),
-    "rgrg_detect": (_i, [c_p, c_p, _i, _i, _i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, C.POINTER(_i), c_p]),
+    "rgrg_detect": (_i, [c_p, c_p, _i, _i, _i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, C.POINTER(_i), c_p]),
     "rgrg_bbox_features": (_i, [c_p, c_p, _i, _i, _i, c_p, c_p, c_p]),
     "rgrg_lm_forced_logits": (_i, [c_p, c_p, _i, c_p, _i, c_p, c_p]),
+    "rgrg_preprocess": (_i, [c_p, c_p, _i, _i, _i, c_p, _i, c_p]),
     "rgrg_greedy_bookkeeping": (_i, [c_p, c_p, _i, _i, _i, c_p, C.POINTER(_i), c_p]),
     "rgrg_beam_bookkeeping": (_i, [c_p, c_p, _i, _i, _i, _i, _i, c_p, C.POINTER(_i), c_p]),
     "rgrg_rpn_filter": (_i, [c_p, c_p, c_p, c_p, _i, _i, _i, c_p, c_p, c_p, c_p, c_p, c_p]),

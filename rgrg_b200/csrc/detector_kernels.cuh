@@ -165,6 +165,63 @@ __global__ void subsample2_kernel(const TAct* __restrict__ in, TAct* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// n3  pre-processing in front of the path (generate_reports_for_images.py:129-147 `get_image_tensor`):
+//   uint8 grayscale [H, W] -> cv2.resize(INTER_AREA) to longest side 512 -> centre zero-pad to 512 x 512 ->
+//   (x - 0.471*255) * (1 / (0.302*255)) -> fp32 [512, 512].  One thread per output pixel; bit-exact against OpenCV:
+//   general (fractional scale) path = computeResizeAreaTab + resizeArea_: per source row the horizontal weighted sum in
+//   table order, then the vertical accumulation in table order, both in fp32 WITHOUT fma contraction, cvRound (half to
+//   even); integer scales = ResizeAreaFast: integer block sum * (1.f / area) -> cvRound, except 2 x 2 (SIMD path):
+//   (sum + 2) >> 2.  Tables are built on the host in double precision exactly like OpenCV (engine.cu).
+// ---------------------------------------------------------------------------------------------------------------
+struct PreprocTab {
+  const int* xoff;    // [nw + 1] CSR offsets into xsi / xal
+  const int* xsi;
+  const float* xal;
+  const int* yoff;    // [nh + 1]
+  const int* ysi;
+  const float* yal;
+  int H, W, nh, nw, top, left;
+  int mode;           // 0 general, 1 integer scale (ix, iy), 2 no resize
+  int ix, iy;
+  float inv_area;     // 1.f / (ix * iy)
+  float mean255, denom;
+};
+
+__global__ void __launch_bounds__(256) preprocess_kernel(const uint8_t* __restrict__ src, PreprocTab t, float* __restrict__ out, int S) {
+  const int ox = blockIdx.x * 32 + (threadIdx.x & 31), oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  if (ox >= S || oy >= S) return;
+  const int rx = ox - t.left, ry = oy - t.top;
+  int v = 0;  // BORDER_CONSTANT, value 0
+  if (rx >= 0 && rx < t.nw && ry >= 0 && ry < t.nh) {
+    if (t.mode == 2) {
+      v = src[static_cast<size_t>(ry) * t.W + rx];
+    } else if (t.mode == 1) {
+      int s = 0;
+      for (int dy = 0; dy < t.iy; ++dy) {
+        const uint8_t* row = src + static_cast<size_t>(ry * t.iy + dy) * t.W + rx * t.ix;
+        for (int dx = 0; dx < t.ix; ++dx) s += row[dx];
+      }
+      v = (t.ix == 2 && t.iy == 2) ? ((s + 2) >> 2) : __float2int_rn(__fmul_rn(static_cast<float>(s), t.inv_area));
+    } else {
+      const int x0 = t.xoff[rx], x1 = t.xoff[rx + 1];
+      float sum = 0.0f;
+      bool first = true;
+      for (int j = t.yoff[ry]; j < t.yoff[ry + 1]; ++j) {
+        const uint8_t* row = src + static_cast<size_t>(t.ysi[j]) * t.W;
+        float buf = 0.0f;
+        for (int k = x0; k < x1; ++k) buf = __fadd_rn(buf, __fmul_rn(static_cast<float>(row[t.xsi[k]]), t.xal[k]));
+        const float term = __fmul_rn(t.yal[j], buf);
+        sum = first ? term : __fadd_rn(sum, term);
+        first = false;
+      }
+      v = __float2int_rn(sum);
+    }
+    v = min(max(v, 0), 255);
+  }
+  out[static_cast<size_t>(oy) * S + ox] = __fmul_rn(__fsub_rn(static_cast<float>(v), t.mean255), t.denom);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // K4-K6  RPN proposal filtering, one CTA per image, no host sync        (torchvision rpn.py:242-297 filter_proposals)
 //   top-k(1000) of the raw objectness (sorted descending, ties -> lowest index)   rpn.py:231-240
 //   analytic anchors (anchor_utils.py:58-133) + BoxCoder.decode weights (1,1,1,1), dw/dh clamp ln(1000/16)
@@ -674,15 +731,17 @@ __global__ void __launch_bounds__(1024) selection_tail_kernel(const float* __res
       for (int k = 0; k < 128; ++k) acc = fmaf(h[k], w[k], acc);
       acc += bias[0];
       logits[r] = acc;
-      sel = (acc > -1.0f) && detected[r];
+      // selection: logit > -1 AND class_detected (binary_classifier_region_selection.py:53-57); abnormal (detected == null):
+      // logit > -1 only, undetected regions are masked later by the caller (binary_classifier_region_abnormal.py:53-57)
+      sel = (acc > -1.0f) && (detected == nullptr || detected[r]);
       selected[r] = static_cast<uint8_t>(sel);
     }
     int tot;
     const int pos = block_exclusive_scan_1024(sel, s_warp, tot);
-    if (sel) sel_rows[run + pos] = r;
+    if (sel && sel_rows) sel_rows[run + pos] = r;
     run += tot;
   }
-  if (threadIdx.x == 0) *num_selected = run;
+  if (threadIdx.x == 0 && num_selected) *num_selected = run;
 }
 
 // gather the selected rows' fp32 features as the bf16 A operand of the decoder's first GEMM; rows [n, round_up(n, 32))

@@ -179,6 +179,7 @@ struct rgrg_engine {
   int opt_detector_precise = 0;  // fp32 detector (parity mode, see run_detect)
   int opt_fused_attn = 1;  // greedy decode: c_attn + KV append + attention as ONE head-aligned kernel (attn_fused.cuh)
   int opt_ln_head = 0;     // LayerNorm (+ split-K reduce + residual) as the cluster-cooperative head of the consumer GEMM
+  int opt_attn_alg = 1;     // fused attention inner loop: 1 = order of dec::attention_dev (bit-identical to the two-kernel path), 2 = lane-per-key
   int opt_attn_warps = 16;  // fused attention: attention / epilogue warps per CTA
   int opt_attn_slots = 2;  // fused attention: shared-memory K/V ring slots per warp
   int opt_l2_ahead = 0;    // fused attention: items whose K/V blocks are prefetched into L2 ahead of the consumer
@@ -193,7 +194,8 @@ struct rgrg_engine {
   float *stem_w = nullptr, *stem_b = nullptr;
   std::vector<BlockW> blocks;
   Linear rpn_conv, rpn_heads, fc6, fc7, pred;
-  LinearF32 dimred, sel0, sel2, sel4;
+  LinearF32 dimred, sel0, sel2, sel4, abn0, abn2, abn4;
+  bool has_abnormal = false;
   Linear fst0, fst2, ukv, lm_head;
   float* wte_f32 = nullptr;
   LayerW layers[NLAYER];
@@ -203,7 +205,7 @@ struct rgrg_engine {
   int ws_B = 0, ws_S = 0;
   DevBuf images, act[2], t1, t2, idb, sub, col, feats, rpn_t, rpn_out;
   DevBuf prop_boxes, prop_scores, prop_count, roi_off, pooled, f6, f7, pred_out;
-  DevBuf detected, top_idx, top_scores, top_boxes, mean2048, trf, s0, s1, sel_logits, selected, sel_rows, num_sel;
+  DevBuf detected, top_idx, top_scores, top_boxes, mean2048, trf, s0, s1, sel_logits, selected, sel_rows, num_sel, abn_logits, abnormal;
   DevBuf lm_in;
   // ---- workspace (decoder)
   int ws_rows = 0, ws_slots = 0;
@@ -224,11 +226,12 @@ struct rgrg_engine {
     if (ev_enter) cudaEventDestroy(ev_enter);
     if (own_stream) cudaStreamDestroy(own_stream);
     for (void* p : weight_allocs) cudaFree(p);
+    for (auto& kv : preproc_tabs) kv.second.buf.release();
     DevBuf* all[] = {&images, &act[0], &act[1], &t1, &t2, &idb, &sub, &col, &feats, &rpn_t, &rpn_out, &prop_boxes,
                      &prop_scores, &prop_count, &roi_off, &pooled, &f6, &f7, &pred_out, &detected, &top_idx,
-                     &top_scores, &top_boxes, &mean2048, &trf, &s0, &s1, &sel_logits, &selected, &sel_rows, &num_sel,
+                     &top_scores, &top_boxes, &mean2048, &trf, &s0, &s1, &sel_logits, &selected, &sel_rows, &num_sel, &abn_logits, &abnormal,
                      &lm_in, &kv_cache, &h, &x, &q, &attn_o, &mlp_mid, &a1, &img, &part_val, &part_idx, &ids,
-                     &unfinished, &unf_count, &step, &logits_tmp, &splitk_parts, &p_act[0], &p_act[1], &p_t1, &p_t2, &p_idb, &p_sub, &p_col, &p_c1, &p_feats, &p_rpn_t, &p_pooled, &p_f6, &p_f7, &b_ids2, &b_anc[0], &b_anc[1], &b_scores, &b_cand_score,
+                     &unfinished, &unf_count, &step, &logits_tmp, &splitk_parts, &preproc_src, &preproc_out, &p_act[0], &p_act[1], &p_t1, &p_t2, &p_idb, &p_sub, &p_col, &p_c1, &p_feats, &p_rpn_t, &p_pooled, &p_f6, &p_f7, &b_ids2, &b_anc[0], &b_anc[1], &b_scores, &b_cand_score,
                      &b_cand_token, &b_cand_beam, &b_hyp_score, &b_hyp_len, &b_hyp_tok, &b_hyp_count, &b_worst, &b_done, &b_not_done};
     for (DevBuf* b : all) b->release();
   }
@@ -635,6 +638,12 @@ struct rgrg_engine {
     sel0 = make_linear_f32("binary_classifier_region_selection.classifier.0");
     sel2 = make_linear_f32("binary_classifier_region_selection.classifier.2");
     sel4 = make_linear_f32("binary_classifier_region_selection.classifier.4");
+    has_abnormal = host.count("binary_classifier_region_abnormal.classifier.0.weight") != 0;
+    if (has_abnormal) {
+      abn0 = make_linear_f32("binary_classifier_region_abnormal.classifier.0");
+      abn2 = make_linear_f32("binary_classifier_region_abnormal.classifier.2");
+      abn4 = make_linear_f32("binary_classifier_region_abnormal.classifier.4");
+    }
     // ---- language model (canonical alias set: language_model.gpt2_blocks.* etc.)
     const std::string lm = "language_model";
     fst0 = make_linear(lm + ".feature_space_transformation_nn.0");
@@ -702,6 +711,106 @@ struct rgrg_engine {
   }
 
   // ================================================================================================================
+  // pre-processing (n3): generate_reports_for_images.py:129-147
+  // ================================================================================================================
+  struct PreprocEntry {
+    det::PreprocTab tab;
+    DevBuf buf;  // one allocation holding all six tables
+  };
+  std::map<std::pair<int, int>, PreprocEntry> preproc_tabs;
+  DevBuf preproc_src, preproc_out;
+
+  // OpenCV computeResizeAreaTab (modules/imgproc/src/resize.cpp), CSR form: entries of dst index d are [off[d], off[d+1])
+  static void area_tab(int ssize, int dsize, std::vector<int>& off, std::vector<int>& si, std::vector<float>& al) {
+    const double scale = 1.0 / (static_cast<double>(dsize) / ssize);
+    off.assign(1, 0);
+    for (int dx = 0; dx < dsize; ++dx) {
+      const double fsx1 = dx * scale, fsx2 = fsx1 + scale;
+      const double cell = std::min(scale, ssize - fsx1);
+      int sx1 = static_cast<int>(std::ceil(fsx1)), sx2 = static_cast<int>(std::floor(fsx2));
+      sx2 = std::min(sx2, ssize - 1);
+      sx1 = std::min(sx1, sx2);
+      if (sx1 - fsx1 > 1e-3) {
+        si.push_back(sx1 - 1);
+        al.push_back(static_cast<float>((sx1 - fsx1) / cell));
+      }
+      for (int sx = sx1; sx < sx2; ++sx) {
+        si.push_back(sx);
+        al.push_back(static_cast<float>(1.0 / cell));
+      }
+      if (fsx2 - sx2 > 1e-3) {
+        si.push_back(sx2);
+        al.push_back(static_cast<float>(std::min(std::min(fsx2 - sx2, 1.0), cell) / cell));
+      }
+      off.push_back(static_cast<int>(si.size()));
+    }
+  }
+  static int py3round(double v) { return static_cast<int>(std::nearbyint(v)); }  // round half to even (default FP mode)
+
+  const det::PreprocTab& preproc_table(int H, int W, int S) {
+    auto key = std::make_pair(H, W);
+    auto it = preproc_tabs.find(key);
+    if (it != preproc_tabs.end()) return it->second.tab;
+    if (std::max(H, W) < S) throw std::runtime_error("pre-processing handles down-scaling only (longest side >= 512)");
+    PreprocEntry& en = preproc_tabs[key];
+    det::PreprocTab& t = en.tab;
+    memset(&t, 0, sizeof(t));
+    // albumentations 1.1.0 longest_max_size: scale = max_size / max(h, w); dims = py3round(dim * scale); no-op if scale == 1
+    const double sc = static_cast<double>(S) / std::max(H, W);
+    t.H = H;
+    t.W = W;
+    t.nh = sc == 1.0 ? H : py3round(H * sc);
+    t.nw = sc == 1.0 ? W : py3round(W * sc);
+    // PadIfNeeded (position = center): top = int((min - rows) / 2.0)
+    t.top = t.nh < S ? static_cast<int>((S - t.nh) / 2.0) : 0;
+    t.left = t.nw < S ? static_cast<int>((S - t.nw) / 2.0) : 0;
+    // Normalize: mean * 255 and reciprocal(std * 255) in float32
+    t.mean255 = 0.471f * 255.0f;
+    t.denom = 1.0f / (0.302f * 255.0f);
+    std::vector<int> xoff, xsi, yoff, ysi;
+    std::vector<float> xal, yal;
+    if (t.nh == H && t.nw == W) {
+      t.mode = 2;
+    } else {
+      const double sx = 1.0 / (static_cast<double>(t.nw) / W), sy = 1.0 / (static_cast<double>(t.nh) / H);
+      const int ix = static_cast<int>(std::nearbyint(sx)), iy = static_cast<int>(std::nearbyint(sy));
+      if (std::abs(sx - ix) < 2.220446049250313e-16 && std::abs(sy - iy) < 2.220446049250313e-16) {
+        t.mode = 1;
+        t.ix = ix;
+        t.iy = iy;
+        t.inv_area = 1.0f / static_cast<float>(ix * iy);
+      } else {
+        t.mode = 0;
+        area_tab(W, t.nw, xoff, xsi, xal);
+        area_tab(H, t.nh, yoff, ysi, yal);
+      }
+    }
+    if (t.mode == 0) {
+      const size_t n_i = xoff.size() + xsi.size() + yoff.size() + ysi.size();
+      const size_t n_f = xal.size() + yal.size();
+      en.buf.ensure((n_i + n_f) * 4);
+      int* di = en.buf.as<int>();
+      auto put_i = [&](const std::vector<int>& v) {
+        CUDA_CHECK(cudaMemcpy(di, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+        int* r = di;
+        di += v.size();
+        return r;
+      };
+      t.xoff = put_i(xoff);
+      t.xsi = put_i(xsi);
+      t.yoff = put_i(yoff);
+      t.ysi = put_i(ysi);
+      float* df = reinterpret_cast<float*>(di);
+      CUDA_CHECK(cudaMemcpy(df, xal.data(), xal.size() * 4, cudaMemcpyHostToDevice));
+      t.xal = df;
+      df += xal.size();
+      CUDA_CHECK(cudaMemcpy(df, yal.data(), yal.size() * 4, cudaMemcpyHostToDevice));
+      t.yal = df;
+    }
+    return t;
+  }
+
+  // ================================================================================================================
   // detector
   // ================================================================================================================
   void ensure_detector_ws(int B, int S) {
@@ -734,6 +843,8 @@ struct rgrg_engine {
     s0.ensure(rows * 512 * 4);
     s1.ensure(rows * 128 * 4);
     sel_logits.ensure(rows * 4);
+    abn_logits.ensure(rows * 4);
+    abnormal.ensure(rows);
     selected.ensure(rows);
     sel_rows.ensure(rows * 4);
     num_sel.ensure(4);
@@ -870,6 +981,7 @@ struct rgrg_engine {
   }
 
   // full detector + selection; leaves lm_in [R,1024] bf16 on the device; returns R
+  bool want_abnormal = false;  // set by rgrg_detect when the caller asks for the abnormal-region predictions
   int run_detect(const float* img_dev, int B, int S, cudaStream_t st) {
     ensure_detector_ws(B, S);
     const int f = S / 32;
@@ -956,6 +1068,15 @@ struct rgrg_engine {
     det::gather_rows_bf16_kernel<<<rows + 31, 256, 0, st>>>(trf.as<float>(), sel_rows.as<int>(), num_sel.as<int>(), lm_in.as<bf16>(), 1024);
     KERNEL_CHECK();
     launches += 5;
+    if (want_abnormal && has_abnormal) {
+      // a9': abnormal classifier (report_generation_model.py:103-106; not evaluated by generate()): same MLP shape
+      simt_f32(trf.as<float>(), abn0.w, rows, 512, 1024, epi<false, ACT_RELU, RES_NONE, true>(s0.p, abn0.bias, 512), st);
+      simt_f32(s0.as<float>(), abn2.w, rows, 128, 512, epi<false, ACT_RELU, RES_NONE, true>(s1.p, abn2.bias, 128), st);
+      det::selection_tail_kernel<<<1, 1024, 0, st>>>(s1.as<float>(), abn4.w, abn4.bias, static_cast<const uint8_t*>(nullptr), abn_logits.as<float>(),
+                                                     abnormal.as<uint8_t>(), static_cast<int*>(nullptr), static_cast<int*>(nullptr), rows);
+      KERNEL_CHECK();
+      launches += 3;
+    }
     int R = 0;
     CUDA_CHECK(cudaMemcpyAsync(&R, num_sel.as<int>(), 4, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));  // report_generation_model.py:260: R == 0 -> return -1
@@ -1021,7 +1142,7 @@ struct rgrg_engine {
   int cluster16_ok = -1;
   bool ln_head_available() {
     if (cluster16_ok < 0) {
-      auto kern = fa::attn_fused_kernel<8, 4, true>;
+      auto kern = fa::attn_fused_kernel<8, 4, true, 1>;
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, fa::Smem<8, 4>::TOTAL);
       cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
       cudaLaunchConfig_t cfg = {};
@@ -1046,13 +1167,16 @@ struct rgrg_engine {
   // (attention warps, ring slots per warp): 48 KB of q/k/v tiles + AW * NSLOT * 4 KB of K/V staging must fit in 227 KB
   template <bool LN_HEAD>
   void launch_attn_fused(const CUtensorMap& tmA, const CUtensorMap& tmW, const fa::Params& fp, cudaStream_t st) {
-    switch (opt_attn_warps * 10 + opt_attn_slots) {
-      case 84: fa::launch<8, 4, LN_HEAD>(tmA, tmW, fp, st, pdl_now); break;
-      case 123: fa::launch<12, 3, LN_HEAD>(tmA, tmW, fp, st, pdl_now); break;
-      case 161: fa::launch<16, 1, LN_HEAD>(tmA, tmW, fp, st, pdl_now); break;
-      case 162: fa::launch<16, 2, LN_HEAD>(tmA, tmW, fp, st, pdl_now); break;
-      case 241: fa::launch<24, 1, LN_HEAD>(tmA, tmW, fp, st, pdl_now); break;
-      default: throw std::runtime_error("unsupported (attn_warps, attn_slots): 8/4, 12/3, 16/1, 16/2, 24/1");
+    switch (opt_attn_alg * 1000 + opt_attn_warps * 10 + opt_attn_slots) {
+      case 1084: fa::launch<8, 4, LN_HEAD, 1>(tmA, tmW, fp, st, pdl_now); break;
+      case 1162: fa::launch<16, 2, LN_HEAD, 1>(tmA, tmW, fp, st, pdl_now); break;
+      case 1241: fa::launch<24, 1, LN_HEAD, 1>(tmA, tmW, fp, st, pdl_now); break;
+      case 2082: fa::launch<8, 2, LN_HEAD, 2>(tmA, tmW, fp, st, pdl_now); break;
+      case 2084: fa::launch<8, 4, LN_HEAD, 2>(tmA, tmW, fp, st, pdl_now); break;
+      case 2122: fa::launch<12, 2, LN_HEAD, 2>(tmA, tmW, fp, st, pdl_now); break;
+      case 2123: fa::launch<12, 3, LN_HEAD, 2>(tmA, tmW, fp, st, pdl_now); break;
+      case 2162: fa::launch<16, 2, LN_HEAD, 2>(tmA, tmW, fp, st, pdl_now); break;
+      default: throw std::runtime_error("unsupported (attn_alg, attn_warps, attn_slots)");
     }
   }
 
@@ -1510,6 +1634,13 @@ int rgrg_create(int device, rgrg_engine_t** out) {
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) throw std::runtime_error("rgrg_b200 requires a Blackwell (sm_100a) GPU; there is no fallback path");
+    // kernel attributes (opt-in shared memory, cluster sizes) and the SM count are cached per process: one engine device
+    // per process, which is the deployment model anyway (one process per GPU)
+    static int process_device = -1;
+    if (process_device >= 0 && process_device != device)
+        throw std::runtime_error("rgrg_b200: this process already drives cuda:" + std::to_string(process_device) +
+                                 "; use one process per GPU (torch.distributed / torchrun)");
+    process_device = device;
     rgrg_engine* e = new rgrg_engine();
     e->device = device;
     const char* ic = getenv("RGRG_IMPLICIT_CONV");
@@ -1557,6 +1688,7 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "ln_head") e->opt_ln_head = value;
   else if (k == "attn_slots") e->opt_attn_slots = value;
   else if (k == "attn_warps") e->opt_attn_warps = value;
+  else if (k == "attn_alg") e->opt_attn_alg = value;
   else if (k == "l2_ahead") e->opt_l2_ahead = value;
   else if (k == "attn_occ") e->opt_attn_occ = value;
   else if (k == "cattn_bn") e->opt_cattn_bn = value;
@@ -1606,12 +1738,22 @@ static void check_ready(rgrg_engine* e) {
 
 int rgrg_detect(rgrg_engine_t* e, const float* images, int images_on_host, int B, int S, uint8_t* out_selected,
                 uint8_t* out_detected, float* out_boxes, float* out_scores, float* out_region_features,
-                int32_t* out_top_idx, int32_t* out_num_proposals, int* out_R, void* stream) {
+                int32_t* out_top_idx, int32_t* out_num_proposals, uint8_t* out_abnormal, int* out_R, void* stream) {
   RGRG_TRY(e, {
     check_ready(e);
+    if (out_abnormal && !e->has_abnormal) throw std::runtime_error("checkpoint has no binary_classifier_region_abnormal weights");
     cudaStream_t st = e->enter(stream);
     const float* img = stage_images(e, images, images_on_host, B, S, st);
-    const int R = e->run_detect(img, B, S, st);
+    e->want_abnormal = out_abnormal != nullptr;
+    int R = 0;
+    try {
+      R = e->run_detect(img, B, S, st);
+    } catch (...) {
+      e->want_abnormal = false;
+      throw;
+    }
+    e->want_abnormal = false;
+    if (out_abnormal) CUDA_CHECK(cudaMemcpyAsync(out_abnormal, e->abnormal.p, static_cast<size_t>(B) * NREG, cudaMemcpyDeviceToHost, st));
     if (out_R) *out_R = R;
     read_detections(e, B, out_selected, out_detected, out_boxes, out_scores, out_region_features, out_top_idx,
                     out_num_proposals, st);
@@ -1700,6 +1842,32 @@ int rgrg_bbox_features(rgrg_engine_t* e, const float* images, int images_on_host
     e->launches += 2;
     CUDA_CHECK(cudaMemcpyAsync(out_features_host, e->trf.p, static_cast<size_t>(rows) * 1024 * 4, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));  // `slots`, `cnt`, `idx` must outlive the copies
+  });
+}
+
+int rgrg_preprocess(rgrg_engine_t* e, const uint8_t* image, int image_on_host, int H, int W, float* out, int out_on_host,
+                    void* stream) {
+  RGRG_TRY(e, {
+    cudaStream_t st = e->enter(stream);
+    constexpr int S = 512;  // IMAGE_INPUT_SIZE, generate_reports_for_images.py:26
+    if (H <= 0 || W <= 0) throw std::runtime_error("bad image size");
+    const det::PreprocTab& tab = e->preproc_table(H, W, S);
+    const uint8_t* src = image;
+    if (image_on_host) {
+      e->preproc_src.ensure(static_cast<size_t>(H) * W);
+      CUDA_CHECK(cudaMemcpyAsync(e->preproc_src.p, image, static_cast<size_t>(H) * W, cudaMemcpyHostToDevice, st));
+      src = e->preproc_src.as<uint8_t>();
+    }
+    float* dst = out;
+    if (out_on_host) {
+      e->preproc_out.ensure(static_cast<size_t>(S) * S * 4);
+      dst = e->preproc_out.as<float>();
+    }
+    det::preprocess_kernel<<<dim3(S / 32, S / 8), 256, 0, st>>>(src, tab, dst, S);
+    KERNEL_CHECK();
+    ++e->launches;
+    if (out_on_host) CUDA_CHECK(cudaMemcpyAsync(out, dst, static_cast<size_t>(S) * S * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
   });
 }
 
@@ -1968,6 +2136,7 @@ int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst, size_t b
     else if (n == "proposals") b = &e->prop_boxes;
     else if (n == "proposal_scores") b = &e->prop_scores;
     else if (n == "selection_logits") b = &e->sel_logits;
+    else if (n == "abnormal_logits") b = &e->abn_logits;
     else if (n == "region_features_2048") b = &e->mean2048;
     else if (n == "fc7") b = &e->f7;
     else if (n.rfind("max_clusters_", 0) == 0) {  // tuning: co-resident clusters of the given size for a 216 KB-smem GEMM CTA

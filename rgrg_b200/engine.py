@@ -104,6 +104,25 @@ class Engine:
         return {"ids": ids[: R.value, : width.value], "R": R.value, "selected": sel.astype(bool),
                 "detected": det.astype(bool), "boxes": boxes, "scores": scores}
 
+    def preprocess(self, images) -> torch.Tensor:
+        """list of uint8 grayscale arrays [H, W] (numpy, host) or CUDA uint8 tensors -> fp32 CUDA tensor [B, 1, 512, 512]
+        (generate_reports_for_images.py:129-147 `get_image_tensor`, batched)."""
+        dev = torch.device("cuda", self.device)
+        out = torch.empty((len(images), 1, 512, 512), dtype=torch.float32, device=dev)
+        for i, im in enumerate(images):
+            if torch.is_tensor(im) and im.is_cuda:
+                im = im.contiguous()
+                assert im.dtype == torch.uint8 and im.dim() == 2
+                on_host, H, W = 0, int(im.shape[0]), int(im.shape[1])
+            else:
+                im = np.ascontiguousarray(im)
+                if im.dtype != np.uint8 or im.ndim != 2:
+                    raise ValueError("pre-processing expects 8-bit single-channel images [H, W]")
+                on_host, H, W = 1, im.shape[0], im.shape[1]
+            self._check(self._lib.rgrg_preprocess(self._h, _ptr(im), on_host, H, W, C.c_void_p(out[i].data_ptr()), 0,
+                                                  _stream(self.device)))
+        return out
+
     def lm_generate(self, feats: torch.Tensor, max_length: int, num_beams: int = 1, early_stopping: bool = False):
         R = int(feats.shape[0])
         on_host = feats.device.type == "cpu"
@@ -114,7 +133,7 @@ class Engine:
                                                int(bool(early_stopping)), _ptr(ids), C.byref(width), _stream(self.device)))
         return ids[:, : width.value]
 
-    def detect(self, images: torch.Tensor):
+    def detect(self, images: torch.Tensor, abnormal: bool = False):
         B, S = int(images.shape[0]), int(images.shape[-1])
         on_host = images.device.type == "cpu"
         images = images.to(torch.float32).contiguous()
@@ -125,12 +144,16 @@ class Engine:
         trf = np.zeros((B, NUM_REGIONS, 1024), dtype=np.float32)
         top_idx = np.zeros((B, NUM_REGIONS), dtype=np.int32)
         nprop = np.zeros((B,), dtype=np.int32)
+        abn = np.zeros((B, NUM_REGIONS), dtype=np.uint8) if abnormal else None
         R = C.c_int(0)
         self._check(self._lib.rgrg_detect(self._h, _ptr(images), int(on_host), B, S, _ptr(sel), _ptr(det), _ptr(boxes),
-                                          _ptr(scores), _ptr(trf), _ptr(top_idx), _ptr(nprop), C.byref(R),
+                                          _ptr(scores), _ptr(trf), _ptr(top_idx), _ptr(nprop), _ptr(abn), C.byref(R),
                                           _stream(self.device)))
-        return {"selected": sel.astype(bool), "detected": det.astype(bool), "boxes": boxes, "scores": scores,
-                "region_features": trf, "top_idx": top_idx, "num_proposals": nprop, "R": R.value}
+        out = {"selected": sel.astype(bool), "detected": det.astype(bool), "boxes": boxes, "scores": scores,
+               "region_features": trf, "top_idx": top_idx, "num_proposals": nprop, "R": R.value}
+        if abnormal:
+            out["predicted_abnormal_regions"] = abn.astype(bool)  # report_generation_model.py:103-106 (eval-mode forward)
+        return out
 
     def bbox_features(self, images: torch.Tensor, boxes) -> np.ndarray:
         """boxes: [B,29,4] (tensor / array / list of 29x4 tensors) -> fp32 [B*29, 1024]"""

@@ -136,6 +136,23 @@ def det_top_idx(oracle_detail, b):
     return out["top_idx"][b].numpy()
 
 
+def test_abnormal_classifier_output(model, images, oracle_detail, synth_sd):
+    """a9': BinaryClassifierRegionAbnormal (eval branch, binary_classifier_region_abnormal.py:53-57) as an extra output of
+    rgrg_detect: `logit > -1`, not masked by class_detected."""
+    eng = model._engine()
+    out = eng.detect(images.cuda(), abnormal=True)
+    feats = torch.from_numpy(out["region_features"])
+    pred, logits = O.region_abnormal(synth_sd, feats, torch.from_numpy(out["detected"]))  # teacher-forced on the engine's features
+    mine = eng.debug_read("abnormal_logits", (2, 29))
+    assert np.abs(mine - logits.numpy()).max() < 1e-4
+    confident = (logits.abs_() if False else (logits + 1).abs()) > 1e-3
+    assert np.array_equal(out["predicted_abnormal_regions"][confident.numpy()], pred.numpy()[confident.numpy()])
+    # and end to end against the oracle's own region features (fp32 decision head on bf16-path features)
+    pred_o, logits_o = O.region_abnormal(synth_sd, oracle_detail["det"]["top_region_features"], oracle_detail["det"]["class_detected"])
+    far = ((logits_o + 1).abs() > 0.2).numpy()
+    assert np.array_equal(out["predicted_abnormal_regions"][far], pred_o.numpy()[far])
+
+
 def test_decoder_logits_teacher_forced(model, synth_sd, oracle_detail):
     """Decoder logits on ORACLE region features and ORACLE tokens: max |dlogit| <= 0.05 (bf16 tolerance,
     SURVEY.md §8(d)); arg-max must agree wherever the oracle's top-1 / top-2 margin exceeds 0.1."""
@@ -207,22 +224,32 @@ def _opts(eng, **kw):
 
 def test_fused_attention_is_bit_identical_to_two_kernel_attention(model, oracle_detail):
     """attn_fused.cuh (c_attn + KV append + attention in one head-aligned kernel) vs c_attn GEMM + attention kernel:
-    same operand rounding and reduction order, so greedy tokens are IDENTICAL — at cache lengths that cross the 16-key
+    with attn_alg 1, same operand rounding and reduction order, so greedy tokens are IDENTICAL — at cache lengths that cross the 16-key
     chunk boundary (L = 17, 33) and for every ring depth."""
     eng = model._engine()
     feats = torch.cat([oracle_detail["sel_feats"]] * 3, 0).contiguous().cuda()  # 174 rows: a full and a partial M tile
     _opts(eng, ln_head=0, fused_attn=0)
     ref = eng.lm_generate(feats, 36)
     try:
-        for warps, slots in ((8, 4), (12, 3), (16, 1), (16, 2), (24, 1)):
+        for warps, slots in ((8, 4), (16, 2), (24, 1)):
             for ahead in (0, 2):
-                _opts(eng, fused_attn=1, attn_warps=warps, attn_slots=slots, l2_ahead=ahead)
+                _opts(eng, fused_attn=1, attn_alg=1, attn_warps=warps, attn_slots=slots, l2_ahead=ahead)
                 out = eng.lm_generate(feats, 36)
                 assert np.array_equal(ref, out), "warps=%d slots=%d l2_ahead=%d" % (warps, slots, ahead)
         _opts(eng, cuda_graph=0)
         assert np.array_equal(ref, eng.lm_generate(feats, 36))
+        # the lane-per-key inner loop (attn_alg 2) sums in a different order: same tokens except at near-ties,
+        # identical across its own launch shapes and under graph replay
+        _opts(eng, cuda_graph=1, attn_alg=2, attn_warps=16, attn_slots=2, l2_ahead=0)
+        a = eng.lm_generate(feats, 36)
+        assert np.array_equal(a[:, :4], ref[:, :4]) and (a == ref).mean() > 0.9
+        for warps, slots in ((8, 2), (8, 4), (12, 2), (12, 3)):
+            _opts(eng, attn_warps=warps, attn_slots=slots)
+            assert np.array_equal(a, eng.lm_generate(feats, 36)), "alg 2 warps=%d slots=%d" % (warps, slots)
+        _opts(eng, cuda_graph=0, attn_warps=16, attn_slots=2)
+        assert np.array_equal(a, eng.lm_generate(feats, 36))
     finally:
-        _opts(eng, cuda_graph=1, fused_attn=1, attn_warps=16, attn_slots=2, l2_ahead=2, ln_head=0)
+        _opts(eng, cuda_graph=1, fused_attn=1, attn_alg=1, attn_warps=16, attn_slots=2, l2_ahead=0, ln_head=0)
 
 
 def test_layernorm_head_matches_separate_layernorm(model, oracle_detail):

@@ -62,6 +62,46 @@ def test_language_model_generate_mirror():
         m.language_model.generate(torch.zeros(4, 1024), max_length=None, num_beams=4)
 
 
+def test_to_normalises_the_device_before_comparing(monkeypatch):
+    """.to("cuda") / .to(torch.device("cuda")) must not tear down a live engine on cuda:0."""
+    from rgrg_b200 import ReportGenerationModel
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    m = ReportGenerationModel(pretrain_without_lm_model=True)
+
+    class _E:
+        closed = False
+
+        def close(self):
+            self.closed = True
+
+    e = _E()
+    m._eng = e
+    m.to("cuda")
+    m.to(torch.device("cuda"))
+    m.to(torch.device("cuda", 0))
+    assert m._eng is e and not e.closed and m.device == torch.device("cuda", 0)
+    m.to("cuda:1")
+    assert e.closed and m._eng is None
+    with pytest.raises(RuntimeError):
+        m.to("cpu")
+
+
+def test_strict_load_reports_missing_keys_and_open_ended_length_is_capped(lm_sd):
+    from rgrg_b200 import ReportGenerationModel
+    from rgrg_b200 import model as M
+
+    with pytest.raises(RuntimeError, match="Missing key"):
+        ReportGenerationModel().load_state_dict(lm_sd)  # decoder-only checkpoint: the detector weights are missing
+    ReportGenerationModel().load_state_dict(lm_sd, strict=False)
+    stub = _StubEngine(R=1)
+    _model(stub).language_model.generate(torch.zeros(2, 1024), max_length=None)
+    assert stub.calls[-1][2] == M.OPEN_ENDED_MAX_LENGTH == 300
+    with pytest.raises(ValueError):
+        _model(stub).generate(torch.zeros(1, 1, 512, 512), max_length=1)
+
+
 def test_generate_without_weights_fails_loudly():
     from rgrg_b200 import ReportGenerationModel
 

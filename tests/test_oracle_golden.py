@@ -55,6 +55,13 @@ def test_selection_matches_reference(golden, lm_sd):
     assert torch.allclose(logits, T(g["logits"]), rtol=0, atol=1e-6)
 
 
+def test_abnormal_classifier_matches_reference(golden, lm_sd):
+    g, a = golden("selection.npz"), golden("abnormal.npz")
+    pred, logits = O.region_abnormal(lm_sd, T(g["top_region_features"]), T(g["class_detected"]))
+    assert torch.equal(pred, T(a["predicted_abnormal_regions"]))
+    assert torch.allclose(logits, T(a["logits"]), rtol=0, atol=1e-6)
+
+
 def test_lm_greedy_matches_reference(golden, lm_sd):
     g = golden("lm_greedy.npz")
     rec = {}

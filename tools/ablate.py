@@ -36,13 +36,12 @@ eng.set_option("ln_head", 0)
 base = run(0)
 print("full step (fused attention, separate LayerNorm): %.3f ms" % base, flush=True)
 if "variants" in sys.argv:
-    for aw, sl in ((8, 4), (12, 3), (16, 1), (24, 1), (16, 2)):
-        for ahead in (0, 2):
-            print("  attn_warps=%d attn_slots=%d l2_ahead=%d : %.3f ms" % (aw, sl, ahead, run(0, attn_warps=aw, attn_slots=sl, l2_ahead=ahead)), flush=True)
+    for alg, aw, sl in ((2, 16, 2), (1, 16, 2)):
+        print("  attn_alg=%d attn_warps=%d attn_slots=%d : %.3f ms" % (alg, aw, sl, run(0, attn_alg=alg, attn_warps=aw, attn_slots=sl)), flush=True)
+    print("  l2_ahead=2 (attn_alg 1, 16/2)     : %.3f ms" % run(0, l2_ahead=2), flush=True)
+    eng.set_option("l2_ahead", 0)
     print("  fused_attn=0 (round 1 step)       : %.3f ms" % run(0, fused_attn=0), flush=True)
-    print("  fused_attn=0 ln_head=1            : %.3f ms" % run(0, ln_head=1), flush=True)
-    print("  fused_attn=1 ln_head=1            : %.3f ms" % run(0, fused_attn=1), flush=True)
-    eng.set_option("ln_head", 0)
+    eng.set_option("fused_attn", 1)
     print("  PDL off                           : %.3f ms" % run(0, pdl=0), flush=True)
     print("  eager, no graph                   : %.3f ms" % run(0, pdl=1, cuda_graph=0), flush=True)
     eng.set_option("cuda_graph", 1)
