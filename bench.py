@@ -250,7 +250,7 @@ def workload_config(args, batch_per_gpu, world):
                         "max_length %d (BASELINE.json %s)" % (args.image_size, args.image_size, batch_per_gpu, mode, args.max_length, which),
             "global_batch": batch_per_gpu * world, "image_size": args.image_size, "max_length": args.max_length,
             "num_beams": args.num_beams,
-            "parallelism": "images sharded over %d GPU(s), no data-path collective; 1 NCCL all-gather of token buffers per step" % world,
+            "parallelism": "images sharded over %d GPU(s), no data-path collective; 1 NCCL all-gather of result blobs per step" % world,
             "weights": "rgrg_b200.synth seed 0 (conditioned random init, SURVEY.md §8(d))",
             "l2": "per-step working set (KV cache + weights + RoI features > 10 GB) >> 126 MB L2; input batch alternates between two seeds"}
 
@@ -279,6 +279,8 @@ def main():
     ap.add_argument("--image-size", type=int, default=512)
     ap.add_argument("--num-beams", type=int, default=1, help="beam search width (BASELINE.json configs[3] uses 4)")
     ap.add_argument("--early-stopping", action="store_true")
+    ap.add_argument("--gather", default="native", choices=["native", "torch"],
+                    help="multi-GPU result gather: the engine's own ncclAllGather (device-side pack) or torch.distributed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -328,10 +330,24 @@ def main():
 
     from rgrg_b200 import parallel
 
+    native_gather = False
+    if world > 1 and args.gather == "native":
+        try:
+            parallel.init_engine_comm(eng, device=dev)  # the engine's own NCCL communicator (rgrg_comm_init)
+            native_gather = True
+        except Exception as exc:  # noqa: BLE001
+            log("engine-side NCCL gather unavailable (%s): using torch.distributed" % exc)
+        flag = torch.tensor([1 if native_gather else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every rank must take the same path
+        native_gather = bool(flag.item())
+
     def collect(out):
-        """C1 of SURVEY.md: one all-gather of the fixed-size per-rank result blob (ids + masks + boxes + scores)."""
+        """C1 of SURVEY.md: one all-gather of the fixed-size per-rank result blob (ids + masks + boxes + scores): packed and
+        gathered by the engine on the device (rgrg_allgather_results), or through torch.distributed on a host-packed blob."""
         if world == 1:
             return out
+        if native_gather:
+            return parallel.all_gather_results_native(eng, B, T)
         return parallel.all_gather_results(out, B, T, device=dev)
 
     def step_device(i):

@@ -98,6 +98,17 @@ RGRG_API int rgrg_bbox_features(rgrg_engine_t* e, const float* images, int image
 RGRG_API int rgrg_lm_forced_logits(rgrg_engine_t* e, const float* feats_dev, int R, const int32_t* forced_ids_dev,
                           int n_tokens, float* out_logits_dev, void* stream);
 
+/* Multi-GPU result gather (the reference has no distributed code).  One process per GPU; rank 0 obtains an
+ * id with rgrg_comm_unique_id and hands it to the other ranks by any means (bench.py: torch.distributed broadcast); every
+ * rank then calls rgrg_comm_init.  rgrg_allgather_results, called right after rgrg_generate with the same B and
+ * max_length, packs this rank's results ON THE DEVICE into the fixed-size blob of rgrg_b200/parallel.py (head [R, width] |
+ * ids int32 [B*29, max_length] padded with 50256 | selected | detected | boxes | scores), runs ONE ncclAllGather
+ * (device to device over NVLink) and copies the world_size blobs to out_host.  NCCL is resolved at run time (dlopen of the
+ * libnccl.so.2 already in the process); the library has no link-time dependency on it. */
+RGRG_API int rgrg_comm_unique_id(void* out_id_128_bytes);
+RGRG_API int rgrg_comm_init(rgrg_engine_t* e, const void* id_128_bytes, int rank, int world);
+RGRG_API int rgrg_allgather_results(rgrg_engine_t* e, int B, int max_length, uint8_t* out_host, size_t blob_bytes, void* stream);
+
 /* Pre-processing in front of the path (replaces `get_image_tensor`, src/full_model/generate_reports_for_images.py:129-147:
  * cv2 INTER_AREA resize to longest side 512 -> centre zero-pad to 512x512 -> (x/255 - 0.471)/0.302), bit-exact against
  * cv2.resize + the albumentations 1.1.0 transforms.  image: uint8 grayscale [H, W] (host or device); out: fp32 [512*512]

@@ -23,6 +23,9 @@ _PROTOTYPES = {
     "rgrg_detect": (_i, [c_p, c_p, _i, _i, _i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, C.POINTER(_i), c_p]),
     "rgrg_bbox_features": (_i, [c_p, c_p, _i, _i, _i, c_p, c_p, c_p]),
     "rgrg_lm_forced_logits": (_i, [c_p, c_p, _i, c_p, _i, c_p, c_p]),
+    "rgrg_comm_unique_id": (_i, [c_p]),
+    "rgrg_comm_init": (_i, [c_p, c_p, _i, _i]),
+    "rgrg_allgather_results": (_i, [c_p, _i, _i, c_p, C.c_size_t, c_p]),
     "rgrg_preprocess": (_i, [c_p, c_p, _i, _i, _i, c_p, _i, c_p]),
     "rgrg_greedy_bookkeeping": (_i, [c_p, c_p, _i, _i, _i, c_p, C.POINTER(_i), c_p]),
     "rgrg_beam_bookkeeping": (_i, [c_p, c_p, _i, _i, _i, _i, _i, c_p, C.POINTER(_i), c_p]),

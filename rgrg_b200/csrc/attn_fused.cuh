@@ -17,9 +17,9 @@
 // 8 dim segments per warp, online softmax in fp32, q / k / v rounded to bf16 exactly where the two-kernel path rounds
 // them — the fused and the two-kernel path produce bit-identical attention outputs.
 //
-// Optional LayerNorm head (cluster of 16 CTAs = the 16 heads of one M tile): instead of a separate LayerNorm kernel,
-// each CTA of the cluster reduces the preceding projection's split-K partial sums into the residual stream and
-// normalises 8 rows of the M tile, the cluster meets at barrier.cluster, and the TMA loads of operand A follow.
+// Optional LayerNorm head (the 16 CTAs = 16 heads of one M tile): instead of a separate LayerNorm kernel, each of the 16
+// CTAs reduces the preceding projection's split-K partial sums into the residual stream and normalises 8 rows of the M
+// tile, the 16 meet at a per-M-tile arrival counter (group_barrier), and the TMA loads of operand A follow.
 #pragma once
 #include "decoder_kernels.cuh"
 #include "epilogues.cuh"
@@ -78,6 +78,8 @@ struct Params {
   const float* parts;    // split-K partial sums of the preceding projection (null: plain LayerNorm of h)
   size_t part_stride;
   const float* res_bias;
+  unsigned* counters;    // [m_tiles] arrival counters of the LayerNorm-head group barrier (common.cuh)
+  int launch_idx, launches_per_step;
 };
 
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -265,9 +267,7 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
         else dec::ln_row_dev<0>(p.h, p.gamma, p.beta, p.x, row, lane, nullptr, 0, nullptr);
       }
     }
-    fence_proxy_async_global();
-    cluster_sync_all();
-    fence_proxy_async_global();
+    group_barrier(p.counters + m_blk, static_cast<unsigned>(*p.step_ptr * p.launches_per_step + p.launch_idx + 1) * 16u);
   }
 
   const int t = *p.step_ptr;
@@ -485,7 +485,6 @@ inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const Params&
   static bool configured = false;  // one engine device per process (rgrg_create enforces it)
   if (!configured) {
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    if (LN_HEAD) CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     configured = true;
   }
   cudaLaunchConfig_t cfg = {};
@@ -498,13 +497,6 @@ inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const Params&
   if (pdl) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
-    ++n;
-  }
-  if (LN_HEAD) {
-    attr[n].id = cudaLaunchAttributeClusterDimension;
-    attr[n].val.clusterDim.x = 16;
-    attr[n].val.clusterDim.y = 1;
-    attr[n].val.clusterDim.z = 1;
     ++n;
   }
   cfg.attrs = attr;

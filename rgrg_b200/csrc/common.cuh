@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include <stdexcept>
 #include <string>
@@ -53,6 +54,31 @@ inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t 
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...));
+}
+
+// Barrier among the `group` CTAs that share one arrival counter (the CTAs of one M tile of a LayerNorm-head kernel), all of
+// them co-resident or scheduled in order.  Counters are monotonic within a generate(): launch number `seq` (0, 1, ...) of
+// the kernels that share the counter waits for (seq + 1) * group arrivals.  Called by every thread of the CTA.
+// Writers' global stores are released by the arrival; the TMA reads that follow go through the async proxy, hence the
+// proxy fences on both sides.
+__device__ __forceinline__ void group_barrier(unsigned* ctr, unsigned target) {
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned old;
+    asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(ctr) : "memory");
+    unsigned v = old + 1;
+    const long long start = clock64();
+    while (v < target) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (clock64() - start > 4000000000LL) {  // ~2 s: a scheduling bug must trap, not hang the GPU
+        printf("rgrg_b200: LayerNorm-head group barrier timed out (block %d, count %u, target %u)\n", blockIdx.x, v, target);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  asm volatile("fence.proxy.async;" ::: "memory");
 }
 
 __device__ __forceinline__ float bf2f(bf16 v) { return __bfloat162float(v); }

@@ -510,6 +510,94 @@ __global__ void __launch_bounds__(1024) beam_topk_kernel(const float* __restrict
   }
 }
 
+// The same selection from the fused lm_head epilogue's per-part summaries (EpiBeamPartial) instead of full logits:
+// per beam row the log-softmax denominator is merged from the (max, sum-exp) pairs, then the 2*nb best of the
+// nb * n_parts * K candidate (logit, token) pairs are chosen exactly like above (score = logit - lse + beam score,
+// ties -> lowest flat index beam * V + token).  One CTA per sentence.
+template <int K>
+__global__ void __launch_bounds__(1024) beam_merge_kernel(const float* __restrict__ part_m, const float* __restrict__ part_l,
+                                                          const float* __restrict__ part_val, const int* __restrict__ part_idx,
+                                                          int n_parts, BeamState s) {
+  __shared__ float s_red[32];
+  __shared__ float s_lse[MAX_BEAMS];
+  __shared__ unsigned long long s_best[32];
+  __shared__ unsigned long long s_pick;
+  const int sent = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = s.nb;
+  for (int b = 0; b < nb; ++b) {
+    const size_t base = static_cast<size_t>(sent * nb + b) * n_parts;
+    float m = -INFINITY;
+    for (int p = tid; p < n_parts; p += 1024) m = fmaxf(m, part_m[base + p]);
+    m = warp_max(m);
+    if (lane == 0) s_red[warp] = m;
+    __syncthreads();
+    m = warp_max(s_red[lane]);
+    __syncthreads();
+    float sum = 0.0f;
+    for (int p = tid; p < n_parts; p += 1024) sum += part_l[base + p] * expf(part_m[base + p] - m);
+    sum = warp_sum(sum);
+    if (lane == 0) s_red[warp] = sum;
+    __syncthreads();
+    sum = warp_sum(s_red[lane]);
+    if (tid == 0) s_lse[b] = m + logf(sum);
+    __syncthreads();
+  }
+  const int KK = 2 * nb;  // <= K
+  unsigned long long loc[2 * MAX_BEAMS];
+#pragma unroll
+  for (int i = 0; i < 2 * MAX_BEAMS; ++i) loc[i] = 0ull;
+  const int total = nb * n_parts * K;
+  for (int j = tid; j < total; j += 1024) {
+    const int b = j / (n_parts * K);
+    const int rest = j - b * (n_parts * K);
+    const size_t o = static_cast<size_t>(sent * nb + b) * n_parts * K + rest;
+    const int tok = part_idx[o];
+    if (tok >= VOCAB) continue;  // empty list slot
+    const float sc = __fadd_rn(__fsub_rn(part_val[o], s_lse[b]), s.beam_scores[sent * nb + b]);
+    const unsigned flat = static_cast<unsigned>(b) * VOCAB + static_cast<unsigned>(tok);
+    const unsigned long long key = (static_cast<unsigned long long>(float_key_dec(sc)) << 32) | (0xFFFFFFFFu - flat);
+    if (key > loc[KK - 1]) {
+      int p = KK - 1;
+      while (p > 0 && loc[p - 1] < key) {
+        loc[p] = loc[p - 1];
+        --p;
+      }
+      loc[p] = key;
+    }
+  }
+  int head = 0;
+  for (int r = 0; r < KK; ++r) {
+    unsigned long long v = head < KK ? loc[head] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ov = __shfl_xor_sync(0xffffffffu, v, o);
+      v = ov > v ? ov : v;
+    }
+    if (lane == 0) s_best[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long w = s_best[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long ov = __shfl_xor_sync(0xffffffffu, w, o);
+        w = ov > w ? ov : w;
+      }
+      if (lane == 0) s_pick = w;
+    }
+    __syncthreads();
+    const unsigned long long pick = s_pick;
+    if (head < KK && loc[head] == pick) ++head;  // keys are unique (they embed the flat index)
+    if (tid == 0) {
+      const unsigned j = 0xFFFFFFFFu - static_cast<unsigned>(pick & 0xFFFFFFFFull);
+      s.cand_score[sent * KK + r] = float_from_key_dec(static_cast<unsigned>(pick >> 32));
+      s.cand_token[sent * KK + r] = static_cast<int>(j % VOCAB);
+      s.cand_beam[sent * KK + r] = static_cast<int>(j / VOCAB);
+    }
+    __syncthreads();
+  }
+}
+
 // BeamSearchScorer.process (one thread per sentence) + the reorder of token rows and cache ancestry
 // (language_model.py:570-589).  next token matrix goes to ids[dst], ancestry to anc[dst].
 __global__ void beam_process_kernel(BeamState s, int sentences, int src, int dst) {

@@ -570,6 +570,81 @@ __global__ void __launch_bounds__(256) roi_align_kernel(const TAct* __restrict__
   }
 }
 
+// Separable form of the same RoIAlign (bf16 fast path, f <= 32).  The kernel above re-reads every feature cell once per
+// bin that touches it: ~16 L2 -> SM bytes per output byte, which makes it L2-throughput-bound (28.8 k RoIs x 1.5 MB).
+// Bilinear weights factor into (row weight) x (column weight), so per bin ROW the vertical interpolation
+//   r[x] = sum_iy wy[iy] * feat[y_iy][x]
+// is computed ONCE per feature column x the row's eight bins touch (a 4-cell circular window per thread in shared memory:
+// a bin's two samples span at most 4 consecutive cells for f <= 32, and the window only moves right), and each bin is
+//   out[py][px] = 0.25 * sum_ix wx[ix] * r[x_ix].
+// ~3x fewer feature loads; same taps and weights, fp32 throughout, summed in (x outer, y inner) order.
+__global__ void __launch_bounds__(256) roi_align_sep_kernel(const bf16* __restrict__ feats, const float* __restrict__ boxes /*[B,1000,4]*/,
+                                                            const int* __restrict__ count, const int* __restrict__ offsets,
+                                                            bf16* __restrict__ out, int f, int C, float scale) {
+  const int b = blockIdx.y, j = blockIdx.x;
+  if (j >= count[b]) return;
+  __shared__ AxisTaps s_y[8], s_x[8];
+  __shared__ float4 s_win[4][2][256];  // [cell & 3][half of the 8 channels][thread]
+  const float* bx = boxes + (static_cast<size_t>(b) * TOPK + j) * 4;
+  if (threadIdx.x < 16) {
+    const float x1 = bx[0] * scale, y1 = bx[1] * scale, x2 = bx[2] * scale, y2 = bx[3] * scale;
+    const float rw = fmaxf(x2 - x1, 1.0f), rh = fmaxf(y2 - y1, 1.0f);
+    if (threadIdx.x < 8) axis_taps(y1, rh / 8.0f, threadIdx.x, f, s_y[threadIdx.x]);
+    else axis_taps(x1, rw / 8.0f, threadIdx.x - 8, f, s_x[threadIdx.x - 8]);
+  }
+  __syncthreads();
+  const bf16* fm = feats + static_cast<size_t>(b) * f * f * C;
+  bf16* dst = out + static_cast<size_t>(offsets[b] + j) * 64 * C;
+  const int tid = threadIdx.x;
+  for (int c0 = tid * 8; c0 < C; c0 += 256 * 8) {
+    for (int py = 0; py < 8; ++py) {
+      const AxisTaps& ty = s_y[py];
+      int have = -1;  // cells <= have (and > have - 4) of this row are in the window
+      auto fill_to = [&](int upto) {  // vertical interpolation of cells have+1 .. upto
+        for (int x = have + 1; x <= upto; ++x) {
+          float r[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) r[e] = 0.0f;
+          for (int iy = 0; iy < ty.n; ++iy) {
+            float fv[8];
+            load8(fm + (static_cast<size_t>(ty.idx[iy]) * f + x) * C + c0, fv);
+            const float w = ty.w[iy];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) r[e] = fmaf(w, fv[e], r[e]);
+          }
+          s_win[x & 3][0][tid] = make_float4(r[0], r[1], r[2], r[3]);
+          s_win[x & 3][1][tid] = make_float4(r[4], r[5], r[6], r[7]);
+        }
+        have = upto;
+      };
+      for (int px = 0; px < 8; ++px) {
+        const AxisTaps& tx = s_x[px];
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+        if (tx.n > 0 && ty.n > 0) {
+          int lo = tx.idx[0], hi = tx.idx[0];
+          for (int q = 1; q < tx.n; ++q) {
+            lo = min(lo, tx.idx[q]);
+            hi = max(hi, tx.idx[q]);
+          }
+          if (have < lo - 1) have = lo - 1;  // cells left of this bin are never needed again
+          if (hi > have) fill_to(hi);
+          for (int q = 0; q < tx.n; ++q) {
+            const float4 a = s_win[tx.idx[q] & 3][0][tid], c = s_win[tx.idx[q] & 3][1][tid];
+            const float w = tx.w[q];
+            acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+            acc[4] = fmaf(w, c.x, acc[4]); acc[5] = fmaf(w, c.y, acc[5]); acc[6] = fmaf(w, c.z, acc[6]); acc[7] = fmaf(w, c.w, acc[7]);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] *= 0.25f;
+        store8(dst + static_cast<size_t>(py * 8 + px) * C + c0, acc);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // K10  per-class top-1 region selection, one CTA per image                          (custom_roi_heads.py:63-208)
 //   softmax(30) -> drop background -> argmax over 29 (first max) -> per class: max score over the RoIs that predict
@@ -798,6 +873,38 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict_
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     out[i] = f2bf(in[i]);
 }
+// Result blob of one rank (layout of rgrg_b200/parallel.py pack_result): [R, width] int32 | ids int32 [rows, T] padded with
+// EOS | selected u8 [rows] | detected u8 [rows] | boxes f32 [rows, 4] | scores f32 [rows]; rows = B * 29.  Byte-wise copies:
+// the tail segments are not 4-byte aligned when rows is odd.
+__global__ void pack_blob_kernel(uint8_t* __restrict__ blob, const int* __restrict__ ids, int ids_ld, int R, int width, int rows, int T,
+                                 const uint8_t* __restrict__ selected, const uint8_t* __restrict__ detected,
+                                 const float* __restrict__ boxes, const float* __restrict__ scores) {
+  const size_t n_ids = static_cast<size_t>(rows) * T;
+  const size_t o_sel = 8 + n_ids * 4, o_det = o_sel + rows, o_box = o_det + rows, o_sc = o_box + static_cast<size_t>(rows) * 16;
+  const size_t total = o_sc + static_cast<size_t>(rows) * 4;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    uint8_t v;
+    if (i < 8) {
+      const int head = i < 4 ? R : width;
+      v = static_cast<uint8_t>(static_cast<unsigned>(head) >> (8 * (i & 3)));
+    } else if (i < o_sel) {
+      const size_t e = (i - 8) >> 2;
+      const int r = static_cast<int>(e / T), c = static_cast<int>(e % T);
+      const int tok = (r < R && c < width) ? ids[static_cast<size_t>(r) * ids_ld + c] : 50256;
+      v = static_cast<uint8_t>(static_cast<unsigned>(tok) >> (8 * ((i - 8) & 3)));
+    } else if (i < o_det) {
+      v = selected[i - o_sel];
+    } else if (i < o_box) {
+      v = detected[i - o_det];
+    } else if (i < o_sc) {
+      v = reinterpret_cast<const uint8_t*>(boxes)[i - o_box];
+    } else {
+      v = reinterpret_cast<const uint8_t*>(scores)[i - o_sc];
+    }
+    blob[i] = v;
+  }
+}
+
 // out[i] = bias[i % N] + sum_s parts[s][i]   (test harness of the split-K GEMM form)
 __global__ void sum_parts_kernel(const float* __restrict__ parts, int nparts, long long total, const float* __restrict__ bias, int N,
                                  float* __restrict__ out) {

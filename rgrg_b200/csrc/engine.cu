@@ -3,6 +3,7 @@
 // object_detector.py:184-261 -> custom_rpn.py:53-85 / custom_roi_heads.py:210-269 ->
 // binary_classifier_region_selection.py:24-68 -> language_model.py:401-479, :609-652).
 #include <cuda.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -94,6 +95,51 @@ struct LayerW {
 
 }  // namespace
 
+// ---- NCCL, resolved at run time from the library already loaded into the process (torch's bundled libnccl.so.2) or the
+// system one: the engine has no link-time dependency on NCCL and builds on a box without it.
+namespace nccl {
+struct UniqueId {
+  char internal[128];
+};
+typedef void* Comm;
+typedef int (*GetUniqueIdFn)(UniqueId*);
+typedef int (*CommInitRankFn)(Comm*, int, UniqueId, int);
+typedef int (*AllGatherFn)(const void*, void*, size_t, int, Comm, cudaStream_t);
+typedef int (*CommDestroyFn)(Comm);
+typedef const char* (*GetErrorStringFn)(int);
+struct Api {
+  GetUniqueIdFn get_unique_id = nullptr;
+  CommInitRankFn comm_init_rank = nullptr;
+  AllGatherFn all_gather = nullptr;
+  CommDestroyFn comm_destroy = nullptr;
+  GetErrorStringFn error_string = nullptr;
+};
+inline const Api& api() {
+  static Api a;
+  static bool loaded = false;
+  if (!loaded) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);  // the copy torch.distributed already loaded
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) throw std::runtime_error("NCCL not found: libnccl.so.2 is neither loaded nor on the library path");
+    a.get_unique_id = reinterpret_cast<GetUniqueIdFn>(dlsym(h, "ncclGetUniqueId"));
+    a.comm_init_rank = reinterpret_cast<CommInitRankFn>(dlsym(h, "ncclCommInitRank"));
+    a.all_gather = reinterpret_cast<AllGatherFn>(dlsym(h, "ncclAllGather"));
+    a.comm_destroy = reinterpret_cast<CommDestroyFn>(dlsym(h, "ncclCommDestroy"));
+    a.error_string = reinterpret_cast<GetErrorStringFn>(dlsym(h, "ncclGetErrorString"));
+    if (!a.get_unique_id || !a.comm_init_rank || !a.all_gather || !a.comm_destroy) throw std::runtime_error("NCCL symbols missing");
+    loaded = true;
+  }
+  return a;
+}
+inline void check(int rc, const char* what) {
+  if (rc != 0) {
+    const Api& a = api();
+    throw std::runtime_error(std::string("NCCL error in ") + what + ": " + (a.error_string ? a.error_string(rc) : std::to_string(rc).c_str()));
+  }
+}
+}  // namespace nccl
+
 struct rgrg_engine;
 struct ProfScope {
   rgrg_engine* e;
@@ -154,6 +200,12 @@ struct rgrg_engine {
     prof_used = 0;
   }
 
+  // ---- result gather across ranks: one ncclAllGather of fixed-size result blobs, device to device
+  nccl::Comm comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+  DevBuf blob_dev, gather_dev;
+  int last_R = 0, last_width = 0, last_T = 0;  // geometry of the ids the last generate() left in `ids` (device)
+
   int device = 0;
   // all work runs on an engine-owned non-blocking stream (the legacy default stream cannot be captured into a CUDA
   // graph); it is ordered after the caller's stream on entry, and every entry point host-synchronises before returning
@@ -179,6 +231,8 @@ struct rgrg_engine {
   int opt_detector_precise = 0;  // fp32 detector (parity mode, see run_detect)
   int opt_fused_attn = 1;  // greedy decode: c_attn + KV append + attention as ONE head-aligned kernel (attn_fused.cuh)
   int opt_ln_head = 0;     // LayerNorm (+ split-K reduce + residual) as the cluster-cooperative head of the consumer GEMM
+  int opt_roi_align_sep = 1;    // RoIAlign in separable form (vertical interpolation once per feature column of a bin row)
+  int opt_beam_fused_head = 1;  // beam search: log-softmax + per-part top-k fused into the lm_head epilogue (0: fp32 logits in HBM)
   int opt_attn_alg = 1;     // fused attention inner loop: 1 = order of dec::attention_dev (bit-identical to the two-kernel path), 2 = lane-per-key
   int opt_attn_warps = 16;  // fused attention: attention / epilogue warps per CTA
   int opt_attn_slots = 2;  // fused attention: shared-memory K/V ring slots per warp
@@ -209,7 +263,7 @@ struct rgrg_engine {
   DevBuf lm_in;
   // ---- workspace (decoder)
   int ws_rows = 0, ws_slots = 0;
-  DevBuf splitk_parts;
+  DevBuf splitk_parts, ln_counters;
   DevBuf kv_cache, h, x, q, attn_o, mlp_mid, a1, img, part_val, part_idx, ids, unfinished, unf_count, step, logits_tmp;
   int last_B = 0, last_S = 0, last_P = 0;
   // beam search: cache-slot ancestry of the current step (null in greedy mode)
@@ -219,8 +273,10 @@ struct rgrg_engine {
   // ---- CUDA graph of one decode step, keyed by row count
   std::map<int, cudaGraphExec_t> step_graphs;
   std::map<int, int> step_graph_nodes;
+  std::map<int, long long> beam_graph_sig;  // buffer addresses a beam graph captured
 
   ~rgrg_engine() {
+    if (comm) nccl::api().comm_destroy(comm);
     for (auto& g : step_graphs) cudaGraphExecDestroy(g.second);
     for (cudaEvent_t ev : prof_pool) cudaEventDestroy(ev);
     if (ev_enter) cudaEventDestroy(ev_enter);
@@ -231,8 +287,8 @@ struct rgrg_engine {
                      &prop_scores, &prop_count, &roi_off, &pooled, &f6, &f7, &pred_out, &detected, &top_idx,
                      &top_scores, &top_boxes, &mean2048, &trf, &s0, &s1, &sel_logits, &selected, &sel_rows, &num_sel, &abn_logits, &abnormal,
                      &lm_in, &kv_cache, &h, &x, &q, &attn_o, &mlp_mid, &a1, &img, &part_val, &part_idx, &ids,
-                     &unfinished, &unf_count, &step, &logits_tmp, &splitk_parts, &preproc_src, &preproc_out, &p_act[0], &p_act[1], &p_t1, &p_t2, &p_idb, &p_sub, &p_col, &p_c1, &p_feats, &p_rpn_t, &p_pooled, &p_f6, &p_f7, &b_ids2, &b_anc[0], &b_anc[1], &b_scores, &b_cand_score,
-                     &b_cand_token, &b_cand_beam, &b_hyp_score, &b_hyp_len, &b_hyp_tok, &b_hyp_count, &b_worst, &b_done, &b_not_done};
+                     &unfinished, &unf_count, &step, &logits_tmp, &splitk_parts, &ln_counters, &blob_dev, &gather_dev, &preproc_src, &preproc_out, &p_act[0], &p_act[1], &p_t1, &p_t2, &p_idb, &p_sub, &p_col, &p_c1, &p_feats, &p_rpn_t, &p_pooled, &p_f6, &p_f7, &b_ids2, &b_anc[0], &b_anc[1], &b_scores, &b_cand_score,
+                     &b_cand_token, &b_cand_beam, &b_hyp_score, &b_hyp_len, &b_hyp_tok, &b_hyp_count, &b_worst, &b_done, &b_not_done, &b_part_m, &b_part_l, &b_part_val, &b_part_idx};
     for (DevBuf* b : all) b->release();
   }
 
@@ -1033,8 +1089,12 @@ struct rgrg_engine {
       if (P_total > 0) {
         {
           ProfScope ps(this, "roi_align", st);
-          det::roi_align_kernel<bf16><<<dim3(TOPK, B), 256, 0, st>>>(feats.as<bf16>(), prop_boxes.as<float>(), prop_count.as<int>(),
+          if (opt_roi_align_sep && f <= 32)
+            det::roi_align_sep_kernel<<<dim3(TOPK, B), 256, 0, st>>>(feats.as<bf16>(), prop_boxes.as<float>(), prop_count.as<int>(),
                                                                      roi_off.as<int>(), pooled.as<bf16>(), f, 2048, scale);
+          else
+            det::roi_align_kernel<bf16><<<dim3(TOPK, B), 256, 0, st>>>(feats.as<bf16>(), prop_boxes.as<float>(), prop_count.as<int>(),
+                                                                       roi_off.as<int>(), pooled.as<bf16>(), f, 2048, scale);
           KERNEL_CHECK();
           ++launches;
         }
@@ -1110,6 +1170,7 @@ struct rgrg_engine {
       attn_o.ensure(rr * DM * 2);
       mlp_mid.ensure(rr * 4 * DM * 2);
       splitk_parts.ensure(rr * DM * 4 * 4);
+      ln_counters.ensure(1024 * 4);
       a1.ensure(rr * DM * 2);
       img.ensure(rr * DM * 2);
       part_val.ensure(rr * 2048 * 4);
@@ -1119,7 +1180,7 @@ struct rgrg_engine {
       unf_count.ensure(static_cast<size_t>(sl + 1) * 4);
       step.ensure(16);
     } catch (...) {
-      DevBuf* all[] = {&kv_cache, &h, &x, &q, &attn_o, &mlp_mid, &splitk_parts, &a1, &img, &part_val, &part_idx, &ids,
+      DevBuf* all[] = {&kv_cache, &h, &x, &q, &attn_o, &mlp_mid, &splitk_parts, &ln_counters, &a1, &img, &part_val, &part_idx, &ids,
                        &unfinished, &unf_count, &step, &logits_tmp};
       for (DevBuf* b : all) b->release();
       ws_rows = ws_slots = 0;
@@ -1203,7 +1264,7 @@ struct rgrg_engine {
     bf16* xp = x.as<bf16>();
     const bool tensor_path = opt_gemm_impl != 2;
     const bool use_fused = opt_fused_attn && !beam_anc && tensor_path;
-    const bool use_head = opt_ln_head && tensor_path && ln_head_available();
+    const bool use_head = opt_ln_head && tensor_path && ceil_div(rows, tc::BM) <= 512;
     // LayerNorm fused with the residual update of the preceding split-K projection (pending_bias != null)
     const float* pending_bias = nullptr;
     auto ln = [&](const float* g, const float* b) {
@@ -1241,6 +1302,9 @@ struct rgrg_engine {
           fp.parts = pending_bias ? parts : nullptr;
           fp.part_stride = pstride;
           fp.res_bias = pending_bias;
+          fp.counters = ln_counters.as<unsigned>();  // first half: the attention kernels' counters
+          fp.launch_idx = l;
+          fp.launches_per_step = NLAYER;
           pending_bias = nullptr;
         } else {
           ln(L.ln1_g, L.ln1_b);
@@ -1275,7 +1339,8 @@ struct rgrg_engine {
       // ---- LN2 + c_fc + gelu_new
       auto ep_fc = epi<true, ACT_GELU_NEW, RES_NONE, true>(mlp_mid.p, L.fc.bias, 4 * DM);
       if (use_head) {
-        tc::GemmShape::LnHead lh{hp, xp, L.ln2_g, L.ln2_b, parts, pstride, pending_bias};
+        tc::GemmShape::LnHead lh{hp, xp, L.ln2_g, L.ln2_b, parts, pstride, pending_bias, ln_counters.as<unsigned>() + 512, sp,
+                                 l, NLAYER};  // second half of the counter array: the c_fc kernels' counters
         pending_bias = nullptr;
         if (!(opt_ablate & 16)) gemm_ln_head("mlp_c_fc", xp, rows, L.fc, ep_fc, lh, st);
       } else {
@@ -1378,6 +1443,44 @@ struct rgrg_engine {
     launches += 3;
   }
 
+  // the same from the fused lm_head epilogue's per-part summaries (generate() path: no [rows, V] logits in HBM)
+  DevBuf b_part_m, b_part_l, b_part_val, b_part_idx;
+  void beam_parts_ensure(int rows, int nb) {
+    const int n_parts = 2 * ceil_div(VOCAB, pick_bn(ceil_div(rows, tc::BM), VOCAB));
+    const int K = nb <= 4 ? 8 : 16;
+    const size_t rp = static_cast<size_t>(rows) * n_parts;
+    b_part_m.ensure(rp * 4);
+    b_part_l.ensure(rp * 4);
+    b_part_val.ensure(rp * K * 4);
+    b_part_idx.ensure(rp * K * 4);
+  }
+  void beam_head_fused(const dec::BeamState& s, int rows, int sentences, int src, cudaStream_t st) {
+    const int bn = pick_bn(ceil_div(rows, tc::BM), VOCAB);
+    const int n_parts = 2 * ceil_div(VOCAB, bn);
+    const int K = s.nb <= 4 ? 8 : 16;
+    if (K == 8) {
+      EpiBeamPartial<8> ep{b_part_m.as<float>(), b_part_l.as<float>(), b_part_val.as<float>(), b_part_idx.as<int>(), n_parts};
+      gemm("lm_head", x.as<bf16>(), rows, lm_head, ep, st, true, bn);
+    } else {
+      EpiBeamPartial<16> ep{b_part_m.as<float>(), b_part_l.as<float>(), b_part_val.as<float>(), b_part_idx.as<int>(), n_parts};
+      gemm("lm_head", x.as<bf16>(), rows, lm_head, ep, st, true, bn);
+    }
+    end_pdl();
+    ProfScope ps(this, "beam_bookkeeping", st);
+    if (K == 8)
+      dec::beam_merge_kernel<8><<<sentences, 1024, 0, st>>>(b_part_m.as<float>(), b_part_l.as<float>(), b_part_val.as<float>(),
+                                                            b_part_idx.as<int>(), n_parts, s);
+    else
+      dec::beam_merge_kernel<16><<<sentences, 1024, 0, st>>>(b_part_m.as<float>(), b_part_l.as<float>(), b_part_val.as<float>(),
+                                                             b_part_idx.as<int>(), n_parts, s);
+    KERNEL_CHECK();
+    dec::beam_process_kernel<<<ceil_div(sentences, 64), 64, 0, st>>>(s, sentences, src, src ^ 1);
+    KERNEL_CHECK();
+    dec::beam_step_end_kernel<<<1, 256, 0, st>>>(s, sentences);
+    KERNEL_CHECK();
+    launches += 3;
+  }
+
   // BeamSearchScorer.finalize on the host (once per generate); returns the reference width
   int beam_finalize(const dec::BeamState& s, int sentences, int cur_len, int final_buf, int max_length, int32_t* out_ids,
                     cudaStream_t st) {
@@ -1449,9 +1552,12 @@ struct rgrg_engine {
     if (nb > dec::MAX_BEAMS) throw std::runtime_error("num_beams > 8 is not supported");
     const int rows = R * nb;
     ensure_decoder_ws(rows, max_length);
-    logits_tmp.ensure(static_cast<size_t>(rows) * VOCAB * 4);
+    const bool fused_head = opt_beam_fused_head && opt_gemm_impl != 2;
+    if (fused_head) beam_parts_ensure(rows, nb);  // before the graph signature below reads the addresses
+    else logits_tmp.ensure(static_cast<size_t>(rows) * VOCAB * 4);
     dec::BeamState s = beam_state(R, nb, max_length, early);
     lm_prologue(feats_bf16, R, nb, st);
+    CUDA_CHECK(cudaMemsetAsync(ln_counters.p, 0, 1024 * 4, st));
     dec::beam_init_kernel<<<ceil_div(rows, 256), 256, 0, st>>>(s, R);
     KERNEL_CHECK();
     ++launches;
@@ -1459,17 +1565,73 @@ struct rgrg_engine {
     int cur = 0, done_steps = 0;
     beam_slots = s.slots;
     beam_nb = nb;
-    for (int t = 0; t < steps; ++t) {
-      beam_anc = s.anc[cur];
-      decode_forward(rows, s.ids[cur], max_length, st);
-      gemm("lm_head", x.as<bf16>(), rows, lm_head, epi<false, ACT_NONE, RES_NONE, false>(logits_tmp.p, nullptr, VOCAB), st, true);
-      end_pdl();
-      beam_bookkeeping(s, logits_tmp.as<float>(), R, cur, st);
-      cur ^= 1;
-      ++done_steps;
-      if ((t & 7) == 7 && t + 1 < steps) {  // beam_scorer.is_done (language_model.py:594) without a per-step sync
+    // one beam step on the buffers of parity `par` (token matrix / ancestry table are double-buffered)
+    auto beam_step = [&](int par) {
+      beam_anc = s.anc[par];
+      decode_forward(rows, s.ids[par], max_length, st);
+      if (fused_head) {
+        beam_head_fused(s, rows, R, par, st);
+      } else {
+        gemm("lm_head", x.as<bf16>(), rows, lm_head, epi<false, ACT_NONE, RES_NONE, false>(logits_tmp.p, nullptr, VOCAB), st, true);
+        end_pdl();
+        beam_bookkeeping(s, logits_tmp.as<float>(), R, par, st);
+      }
+    };
+    // CUDA graph of TWO consecutive steps (parity 0 then 1), replayed from step 2 on; keyed by the geometry and by the
+    // buffer addresses it captured
+    cudaGraphExec_t exec = nullptr;
+    int nodes = 0;
+    const long long sig = reinterpret_cast<long long>(s.ids[1]) ^ (reinterpret_cast<long long>(s.anc[0]) << 1) ^
+                          (reinterpret_cast<long long>(fused_head ? b_part_val.p : logits_tmp.p) << 2) ^ (reinterpret_cast<long long>(s.hyp_tok) << 3);
+    const int graph_key = -(((rows * 4096 + max_length) * 16 + nb) * 2 + (early ? 1 : 0));  // negative: beam graphs
+    const bool want_graph = opt_cuda_graph && !prof_on && steps >= 6;
+    int t = 0;
+    while (t < steps) {
+      if (want_graph && !exec && t == 2) {
+        auto it = step_graphs.find(graph_key);
+        if (it != step_graphs.end() && beam_graph_sig[graph_key] == sig) {
+          exec = it->second;
+          nodes = step_graph_nodes[graph_key];
+        } else {
+          if (it != step_graphs.end()) {
+            cudaGraphExecDestroy(it->second);
+            step_graphs.erase(it);
+          }
+          cudaGraph_t graph;
+          const int64_t saved = launches;
+          CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+          try {
+            beam_step(0);
+            beam_step(1);
+          } catch (...) {
+            cudaGraph_t dead;
+            cudaStreamEndCapture(st, &dead);
+            throw;
+          }
+          CUDA_CHECK(cudaStreamEndCapture(st, &graph));
+          nodes = static_cast<int>(launches - saved);
+          launches = saved;
+          CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+          CUDA_CHECK(cudaGraphDestroy(graph));
+          step_graphs[graph_key] = exec;
+          step_graph_nodes[graph_key] = nodes;
+          beam_graph_sig[graph_key] = sig;
+        }
+      }
+      if (exec && (t & 1) == 0 && t + 1 < steps) {
+        CUDA_CHECK(cudaGraphLaunch(exec, st));
+        launches += nodes;
+        t += 2;
+        done_steps += 2;  // cur is unchanged after an even number of steps
+      } else {
+        beam_step(cur);
+        cur ^= 1;
+        ++t;
+        ++done_steps;
+      }
+      if (((t - 1) & 7) == 7 && t < steps) {  // beam_scorer.is_done (language_model.py:594) without a per-step sync
         int c = 1;
-        CUDA_CHECK(cudaMemcpyAsync(&c, s.not_done_count + t, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(&c, s.not_done_count + (t - 1), 4, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         if (c == 0) break;
       }
@@ -1510,6 +1672,7 @@ struct rgrg_engine {
     g.step_ptr = step.as<int>();
     g.ticket = step.as<int>() + 1;
     g.live_rows = R;
+    CUDA_CHECK(cudaMemsetAsync(ln_counters.p, 0, 1024 * 4, st));
     dec::greedy_init_kernel<<<ceil_div(std::max(Rp, max_length), 256), 256, 0, st>>>(g, Rp);
     KERNEL_CHECK();
     ++launches;
@@ -1689,6 +1852,8 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "attn_slots") e->opt_attn_slots = value;
   else if (k == "attn_warps") e->opt_attn_warps = value;
   else if (k == "attn_alg") e->opt_attn_alg = value;
+  else if (k == "beam_fused_head") e->opt_beam_fused_head = value;
+  else if (k == "roi_align_sep") e->opt_roi_align_sep = value;
   else if (k == "l2_ahead") e->opt_l2_ahead = value;
   else if (k == "attn_occ") e->opt_attn_occ = value;
   else if (k == "cattn_bn") e->opt_cattn_bn = value;
@@ -1776,6 +1941,12 @@ int rgrg_generate(rgrg_engine_t* e, const float* images, int images_on_host, int
       width = num_beams == 1 ? e->run_greedy(e->lm_in.as<bf16>(), R, max_length, out_ids, st)
                              : e->run_beam(e->lm_in.as<bf16>(), R, num_beams, max_length, early_stopping != 0, out_ids, st);
     if (out_width) *out_width = width;
+    // keep the final ids on the device for rgrg_allgather_results (greedy: they already are; beam: finalize ran on the host)
+    if (R > 0 && num_beams > 1)
+      CUDA_CHECK(cudaMemcpyAsync(e->ids.p, out_ids, static_cast<size_t>(R) * max_length * 4, cudaMemcpyHostToDevice, st));
+    e->last_R = R;
+    e->last_width = width;
+    e->last_T = max_length;
     read_detections(e, B, out_selected, out_detected, out_boxes, out_scores, nullptr, nullptr, nullptr, st);
   });
 }
@@ -1871,6 +2042,54 @@ int rgrg_preprocess(rgrg_engine_t* e, const uint8_t* image, int image_on_host, i
   });
 }
 
+int rgrg_comm_unique_id(void* out_id_128_bytes) {
+  try {
+    nccl::UniqueId id;
+    nccl::check(nccl::api().get_unique_id(&id), "ncclGetUniqueId");
+    memcpy(out_id_128_bytes, &id, sizeof(id));
+    return 0;
+  } catch (const std::exception& ex) {
+    g_create_error = ex.what();
+    return 1;
+  }
+}
+
+int rgrg_comm_init(rgrg_engine_t* e, const void* id_128_bytes, int rank, int world) {
+  RGRG_TRY(e, {
+    if (world < 1 || rank < 0 || rank >= world) throw std::runtime_error("bad rank / world size");
+    if (e->comm) {
+      nccl::api().comm_destroy(e->comm);
+      e->comm = nullptr;
+    }
+    nccl::UniqueId id;
+    memcpy(&id, id_128_bytes, sizeof(id));
+    nccl::check(nccl::api().comm_init_rank(&e->comm, world, id, rank), "ncclCommInitRank");
+    e->comm_rank = rank;
+    e->comm_world = world;
+  });
+}
+
+int rgrg_allgather_results(rgrg_engine_t* e, int B, int max_length, uint8_t* out_host, size_t blob_bytes, void* stream) {
+  RGRG_TRY(e, {
+    if (!e->comm) throw std::runtime_error("rgrg_comm_init has not been called");
+    const int rows = B * NREG;
+    const size_t need = 8 + static_cast<size_t>(rows) * max_length * 4 + 2 * static_cast<size_t>(rows) + static_cast<size_t>(rows) * 20;
+    if (blob_bytes != need) throw std::runtime_error("blob size does not match (B, max_length)");
+    if (B != e->last_B || max_length != e->last_T) throw std::runtime_error("rgrg_allgather_results must follow rgrg_generate with the same B and max_length");
+    cudaStream_t st = e->enter(stream);
+    e->blob_dev.ensure(need);
+    e->gather_dev.ensure(need * e->comm_world);
+    det::pack_blob_kernel<<<rgrg_engine::grid_for(static_cast<long long>(need)), 256, 0, st>>>(
+        e->blob_dev.as<uint8_t>(), e->ids.as<int>(), max_length, e->last_R, e->last_width, rows, max_length, e->selected.as<uint8_t>(),
+        e->detected.as<uint8_t>(), e->top_boxes.as<float>(), e->top_scores.as<float>());
+    KERNEL_CHECK();
+    ++e->launches;
+    nccl::check(nccl::api().all_gather(e->blob_dev.p, e->gather_dev.p, need, /*ncclUint8*/ 1, e->comm, st), "ncclAllGather");
+    CUDA_CHECK(cudaMemcpyAsync(out_host, e->gather_dev.p, need * e->comm_world, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
 int rgrg_lm_forced_logits(rgrg_engine_t* e, const float* feats_dev, int R, const int32_t* forced_ids_dev, int n_tokens,
                           float* out_logits_dev, void* stream) {
   RGRG_TRY(e, {
@@ -1888,6 +2107,7 @@ int rgrg_lm_forced_logits(rgrg_engine_t* e, const float* feats_dev, int R, const
     g.ticket = e->step.as<int>() + 1;
     g.live_rows = R;
     g.forced = forced_ids_dev;
+    CUDA_CHECK(cudaMemsetAsync(e->ln_counters.p, 0, 1024 * 4, st));
     dec::greedy_init_kernel<<<ceil_div(std::max(R, n_tokens), 256), 256, 0, st>>>(g, R);
     KERNEL_CHECK();
     ++e->launches;
@@ -1962,8 +2182,12 @@ int rgrg_roi_align(rgrg_engine_t* e, const void* feats_bf16_dev, const float* bo
     e->roi_off.ensure(static_cast<size_t>(B + 1) * 4);
     det::roi_offsets_kernel<<<1, 32, 0, st>>>(count_dev, e->roi_off.as<int>(), B);
     const float scale = exp2f(roundf(log2f(static_cast<float>(feat) / static_cast<float>(image_size))));
-    det::roi_align_kernel<bf16><<<dim3(TOPK, B), 256, 0, st>>>(static_cast<const bf16*>(feats_bf16_dev), boxes_dev, count_dev,
-                                                        e->roi_off.as<int>(), static_cast<bf16*>(out_bf16_dev), feat, C, scale);
+    if (e->opt_roi_align_sep && feat <= 32)
+      det::roi_align_sep_kernel<<<dim3(TOPK, B), 256, 0, st>>>(static_cast<const bf16*>(feats_bf16_dev), boxes_dev, count_dev,
+                                                               e->roi_off.as<int>(), static_cast<bf16*>(out_bf16_dev), feat, C, scale);
+    else
+      det::roi_align_kernel<bf16><<<dim3(TOPK, B), 256, 0, st>>>(static_cast<const bf16*>(feats_bf16_dev), boxes_dev, count_dev,
+                                                                 e->roi_off.as<int>(), static_cast<bf16*>(out_bf16_dev), feat, C, scale);
     KERNEL_CHECK();
     e->launches += 2;
     CUDA_CHECK(cudaStreamSynchronize(st));

@@ -218,4 +218,74 @@ struct EpiArgmaxPartial {
   }
 };
 
+// lm_head epilogue for beam search (language_model.py:556-568): instead of materialising [rows, 50257] fp32 logits
+// (746 MB per step at 3712 rows) every epilogue thread emits, for the 128 columns it saw of its row, the online
+// (max, sum of exp) pair of the log-softmax denominator and its K best (logit, token) pairs, K = 2 * num_beams.
+// log_softmax(x) + beam_score is monotone in x within a row, so the sentence's top 2 * num_beams over num_beams * V
+// candidates are among these per-part lists; dec::beam_merge_kernel combines them.
+template <int K>
+struct EpiBeamPartial {
+  struct State {
+    float m, l;
+    float val[K];
+    int idx[K];
+  };
+  static constexpr bool kDirect = true;
+  float* part_m;    // [M, n_parts]
+  float* part_l;    // [M, n_parts]
+  float* part_val;  // [M, n_parts, K] descending
+  int* part_idx;    // [M, n_parts, K]
+  int n_parts;
+
+  __device__ __forceinline__ void init(State& s, int) const {
+    s.m = -INFINITY;
+    s.l = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      s.val[k] = -INFINITY;
+      s.idx[k] = 0x7fffffff;
+    }
+  }
+  template <int NV>
+  __device__ __forceinline__ void apply(State& s, int row, int col0, const float* v, int N) const {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      if (col0 + j < N) {
+        const float x = v[j];
+        if (x > s.m) {
+          s.l = s.l * __expf(s.m - x) + 1.0f;
+          s.m = x;
+        } else {
+          s.l += __expf(x - s.m);
+        }
+        if (x > s.val[K - 1]) {  // strict: on equal logits the lower token index (seen first) stays ahead
+          float cv = x;
+          int ci = col0 + j;
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            if (cv > s.val[k]) {
+              const float tv = s.val[k];
+              const int ti = s.idx[k];
+              s.val[k] = cv;
+              s.idx[k] = ci;
+              cv = tv;
+              ci = ti;
+            }
+          }
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void finish(State& s, int row, int part) const {
+    const size_t o = static_cast<size_t>(row) * n_parts + part;
+    part_m[o] = s.m;
+    part_l[o] = s.l;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      part_val[o * K + k] = s.val[k];
+      part_idx[o * K + k] = s.idx[k];
+    }
+  }
+};
+
 }  // namespace rgrg

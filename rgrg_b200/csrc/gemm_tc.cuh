@@ -34,9 +34,11 @@ struct GemmShape {
   int tiles_w, tiles_h;  // output tiles per image: (W/16) x (H/8); one tile = 8 rows x 16 cols = 128 pixels
   long long* trace;      // optional [grid, 8] clock64 timeline of each CTA (bring-up / tuning only)
   int k_splits;          // split-K factor (0/1 = off): tile index -> (split, m, n); each split covers k_iters / k_splits blocks
-  // Optional LayerNorm head (launched as clusters of 16 CTAs = the 16 N tiles of one M tile, one tile per CTA, m_fastest = 0):
-  // before the main loop CTA `n_blk` reduces the preceding projection's split-K partial sums into the residual stream and
-  // normalises rows [m_blk*128 + n_blk*8, +8) into `x` (this GEMM's own operand A); the cluster meets at barrier.cluster.
+  // Optional LayerNorm head (16 N tiles per M tile, one tile per CTA, m_fastest = 0 so the 16 CTAs of an M tile are
+  // consecutive): before the main loop CTA `n_blk` reduces the preceding projection's split-K partial sums into the residual
+  // stream and normalises rows [m_blk*128 + n_blk*8, +8) into `x` (this GEMM's own operand A); the 16 CTAs then meet at a
+  // per-M-tile arrival counter (group_barrier, common.cuh).  (A 16-CTA cluster with barrier.cluster was measured first:
+  // only 7 such clusters fit on a B200 at this shared-memory size, so 8 M tiles ran as two waves.)
   struct LnHead {
     float* h;             // fp32 residual stream [M, 1024]; null = no head
     bf16* x;              // normalised bf16 rows [M, 1024]
@@ -45,6 +47,9 @@ struct GemmShape {
     const float* parts;   // split-K partial sums [4][M, 1024] of the preceding projection (null: plain LayerNorm)
     size_t part_stride;
     const float* res_bias;
+    unsigned* counters;   // [m_tiles] arrival counters, zeroed at the start of a generate()
+    const int* step_ptr;  // device decode step: barrier targets derive from it, so a captured graph can be replayed
+    int launch_idx, launches_per_step;  // this launch's position among the launches of a step that share the counters
   } lnh;
 };
 
@@ -487,9 +492,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       const int row = t0.m_blk * BM + t0.n_blk * 8 + (warp - 2);
       if (row < s.M) ln_head_row(s.lnh.h, s.lnh.gamma, s.lnh.beta, s.lnh.x, row, lane, s.lnh.parts, s.lnh.part_stride, s.lnh.res_bias);
     }
-    asm volatile("fence.proxy.async;" ::: "memory");
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    asm volatile("fence.proxy.async;" ::: "memory");
+    group_barrier(s.lnh.counters + t0.m_blk,
+                  static_cast<unsigned>(*s.lnh.step_ptr * s.lnh.launches_per_step + s.lnh.launch_idx + 1) * 16u);
   }
   if (warp == 0) {
     if (lane == 0) pipe.produce(&tmA, &tmB, s, kbg, prefetched);
@@ -564,16 +568,16 @@ inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmSha
                    cudaStream_t stream, bool pdl = false) {
   using L = SmemLayout<BN, STAGES>;
   auto kern = gemm_tc_kernel<BN, STAGES, Epi, LN_HEAD>;
-  constexpr int cluster = LN_HEAD ? 16 : 1;
+  constexpr int cluster = 1;
   static bool configured = false;  // one static per template instantiation; one engine device per process (rgrg_create)
   if (!configured) {
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    if (LN_HEAD) CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     configured = true;
   }
   const int tiles = s.m_tiles * s.n_tiles * (s.k_splits > 1 ? s.k_splits : 1);
-  // cluster launch (LayerNorm head): one tile per CTA, so that cluster rank == N tile
-  const int grid = cluster > 1 ? tiles : (tiles < num_sms() ? tiles : num_sms());
+  // LayerNorm head: one tile per CTA (CTA index == tile index; CTAs are scheduled in index order, so the 16 CTAs of an M
+  // tile that meet at the group barrier become resident together)
+  const int grid = LN_HEAD ? tiles : (tiles < num_sms() ? tiles : num_sms());
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NUM_THREADS);

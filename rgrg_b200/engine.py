@@ -104,6 +104,30 @@ class Engine:
         return {"ids": ids[: R.value, : width.value], "R": R.value, "selected": sel.astype(bool),
                 "detected": det.astype(bool), "boxes": boxes, "scores": scores}
 
+    # ---- multi-GPU result gather (one ncclAllGather issued by the engine, device to device)
+    def comm_init(self, rank: int, world: int, broadcast_bytes):
+        """broadcast_bytes(buf: bytearray-like uint8 tensor of 128 bytes, src=0): fills `buf` on every rank with rank 0's
+        content (e.g. a torch.distributed broadcast)."""
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = np.zeros(128, dtype=np.uint8)
+            if self._lib.rgrg_comm_unique_id(_ptr(buf)) != 0:
+                raise RuntimeError(self._lib.rgrg_last_error(None).decode())
+            ident = torch.from_numpy(buf)
+        ident = broadcast_bytes(ident)
+        ident = np.ascontiguousarray(ident.cpu().numpy())
+        self._check(self._lib.rgrg_comm_init(self._h, _ptr(ident), int(rank), int(world)))
+        self._world = int(world)
+
+    def allgather_results(self, batch: int, max_length: int) -> np.ndarray:
+        """-> uint8 [world, blob_bytes]: the packed results (rgrg_b200.parallel layout) of the last generate() of every rank."""
+        from . import parallel
+
+        n = parallel.blob_bytes(batch, max_length)
+        out = np.zeros((self._world, n), dtype=np.uint8)
+        self._check(self._lib.rgrg_allgather_results(self._h, int(batch), int(max_length), _ptr(out), n, _stream(self.device)))
+        return out
+
     def preprocess(self, images) -> torch.Tensor:
         """list of uint8 grayscale arrays [H, W] (numpy, host) or CUDA uint8 tensors -> fp32 CUDA tensor [B, 1, 512, 512]
         (generate_reports_for_images.py:129-147 `get_image_tensor`, batched)."""

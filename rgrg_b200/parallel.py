@@ -82,3 +82,24 @@ def all_gather_results(out: Dict, batch: int, max_length: int, device=None) -> D
     flat = buf.cpu().numpy()
     n = blob.numel()
     return merge_results([unpack_result(flat[r * n:(r + 1) * n], batch, max_length) for r in range(world)])
+
+
+def init_engine_comm(engine, device=None):
+    """Create the engine's own NCCL communicator (rgrg_comm_init): rank 0's ncclUniqueId travels through the already
+    initialised torch.distributed group (any backend)."""
+    import torch.distributed as dist
+
+    def bcast(buf):
+        t = buf.to(device) if (device is not None and dist.get_backend() == "nccl") else buf
+        dist.broadcast(t, src=0)
+        return t
+
+    engine.comm_init(dist.get_rank(), dist.get_world_size(), bcast)
+
+
+def all_gather_results_native(engine, batch: int, max_length: int) -> Dict:
+    """The same merge as all_gather_results, with pack + all-gather done by the engine on the device
+    (rgrg_allgather_results: one ncclAllGather, no host-side packing, no torch tensors on the data path)."""
+    blobs = engine.allgather_results(batch, max_length)
+    return merge_results([unpack_result(blobs[r], batch, max_length) for r in range(blobs.shape[0])])
+

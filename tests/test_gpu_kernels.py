@@ -120,7 +120,9 @@ def test_rpn_decode_on_device_matches_reference(eng, golden):
         assert abs(n - int(g["count"][b])) <= 2
 
 
-def test_roi_align_matches_reference_kernel(eng, golden):
+@pytest.mark.parametrize("separable", [1, 0])
+def test_roi_align_matches_reference_kernel(eng, golden, separable):
+    eng.set_option("roi_align_sep", separable)
     g = golden("roi_align.npz")
     feats = T(g["feats"]).permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()  # NHWC
     rois = [T(g["rois0"]), T(g["rois1"])]
@@ -138,6 +140,41 @@ def test_roi_align_matches_reference_kernel(eng, golden):
     # and against the reference's fp32 output, looser (input + output rounding)
     ref32 = T(g["pooled"]).permute(0, 2, 3, 1).reshape(ref.shape[0], 64, -1)
     assert (out.float().cpu() - ref32).abs().max().item() < 0.03 * max(1.0, ref32.abs().max().item())
+    eng.set_option("roi_align_sep", 1)
+
+
+def test_roi_align_separable_edge_boxes(eng):
+    """Boxes that leave the image, degenerate (zero-size) boxes, full-image boxes and sub-cell boxes: the separable kernel
+    against torchvision's kernel on bf16-rounded inputs, 16x16 and 32x32 maps."""
+    import torchvision
+
+    for f, S in ((16, 512), (32, 1024)):
+        g = torch.Generator().manual_seed(f)
+        feats = torch.randn(2, f, f, 64, generator=g).to(torch.bfloat16)
+        rois = []
+        for b in range(2):
+            r = torch.rand(40, 4, generator=g) * S
+            x1, x2 = torch.minimum(r[:, 0], r[:, 2]), torch.maximum(r[:, 0], r[:, 2])
+            y1, y2 = torch.minimum(r[:, 1], r[:, 3]), torch.maximum(r[:, 1], r[:, 3])
+            bx = torch.stack([x1, y1, x2, y2], 1)
+            bx[0] = torch.tensor([0.0, 0.0, float(S), float(S)])       # whole image
+            bx[1] = torch.tensor([100.0, 100.0, 100.0, 100.0])         # zero size
+            bx[2] = torch.tensor([S - 3.0, S - 3.0, float(S), float(S)])  # corner, sub-cell
+            bx[3] = torch.tensor([0.0, 200.0, 5.0, 204.0])             # thin
+            bx[4] = torch.tensor([10.0, 20.0, S - 1.0, 60.0])          # wide
+            rois.append(bx)
+        boxes = torch.zeros(2, 1000, 4)
+        for b in range(2):
+            boxes[b, :40] = rois[b]
+        count = torch.tensor([40, 40], dtype=torch.int32)
+        ref = torchvision.ops.roi_align(feats.float().permute(0, 3, 1, 2), rois, (8, 8), f / S, 2)
+        ref = ref.permute(0, 2, 3, 1).reshape(80, 64, -1)
+        for sep in (1, 0):
+            eng.set_option("roi_align_sep", sep)
+            out = eng.roi_align(feats.cuda(), boxes.cuda(), count.cuda(), image_size=S)
+            err = (out.float().cpu() - ref).abs().max().item()
+            assert err < 0.02 * max(1.0, ref.abs().max().item()), (f, sep, err)
+    eng.set_option("roi_align_sep", 1)
 
 
 def test_roi_tail_bit_exact_on_reference_vectors(eng, golden):

@@ -217,6 +217,36 @@ def test_beam_search_end_to_end_contract(model, synth_sd, oracle_detail):
     assert (ids.cpu() == ref).float().mean().item() > 0.5
 
 
+def test_beam_search_graph_replay_equals_eager(model, oracle_detail):
+    """Beam steps replayed as a CUDA graph of two steps (double-buffered token / ancestry tables) vs eager launches, with
+    and without early stopping, odd and even step counts."""
+    eng = model._engine()
+    feats = oracle_detail["sel_feats"][:7].contiguous().cuda()
+    for T, es in ((12, True), (13, False), (20, True)):
+        eng.set_option("cuda_graph", 1)
+        a = eng.lm_generate(feats, T, num_beams=4, early_stopping=es)
+        b = eng.lm_generate(feats, T, num_beams=4, early_stopping=es)  # cached graph
+        eng.set_option("cuda_graph", 0)
+        c = eng.lm_generate(feats, T, num_beams=4, early_stopping=es)
+        eng.set_option("cuda_graph", 1)
+        assert np.array_equal(a, b) and np.array_equal(a, c), (T, es)
+
+
+def test_beam_fused_head_matches_logits_path(model, oracle_detail):
+    """Beam search with log-softmax + per-part top-k fused into the lm_head epilogue (no [rows, V] logits in HBM) vs the
+    path that stores fp32 logits: same candidates; the log-softmax denominator is summed in a different order (1e-7), so
+    only a near-tie may flip.  num_beams 4 (K = 8 lists) and 6 (K = 16 lists)."""
+    eng = model._engine()
+    feats = oracle_detail["sel_feats"][:9].contiguous().cuda()
+    for nb in (4, 6):
+        eng.set_option("beam_fused_head", 0)
+        a = eng.lm_generate(feats, 14, num_beams=nb, early_stopping=True)
+        eng.set_option("beam_fused_head", 1)
+        b = eng.lm_generate(feats, 14, num_beams=nb, early_stopping=True)
+        assert a.shape == b.shape
+        assert np.array_equal(a[:, :3], b[:, :3]) and (a == b).mean() > 0.9, nb
+
+
 def _opts(eng, **kw):
     for k, v in kw.items():
         eng.set_option(k, v)

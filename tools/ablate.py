@@ -42,6 +42,10 @@ if "variants" in sys.argv:
     eng.set_option("l2_ahead", 0)
     print("  fused_attn=0 (round 1 step)       : %.3f ms" % run(0, fused_attn=0), flush=True)
     eng.set_option("fused_attn", 1)
+    print("  ln_head=1 (group barrier)         : %.3f ms" % run(0, ln_head=1), flush=True)
+    print("  ln_head=1 fused_attn=0            : %.3f ms" % run(0, fused_attn=0), flush=True)
+    eng.set_option("fused_attn", 1)
+    eng.set_option("ln_head", 0)
     print("  PDL off                           : %.3f ms" % run(0, pdl=0), flush=True)
     print("  eager, no graph                   : %.3f ms" % run(0, pdl=1, cuda_graph=0), flush=True)
     eng.set_option("cuda_graph", 1)

@@ -55,6 +55,46 @@ def full_report(rep_path, out_path, title, note):
             f.write("\n")
 
 
+WANT2 = [("gpu__time_duration.sum", "duration"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
+         ("launch__registers_per_thread", "regs"), ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
+         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM %"), ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
+         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor % (elapsed)"),
+         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor % (active)"),
+         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active %"),
+         ("l1tex__m_xbar2l1tex_read_bytes.sum", "L2->SM read")]
+
+
+def wide_table(rep_path, out_path, title, note, skip=()):
+    """one row per captured launch, one column per metric"""
+    out = subprocess.run(["ncu", "-i", rep_path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    with open(out_path, "w") as f:
+        f.write("# %s\n\n%s\n\n" % (title, note))
+        f.write("| kernel | " + " | ".join(w[1] for w in WANT2) + " |\n|---|" + "---:|" * len(WANT2) + "\n")
+        for r in rows[2:]:
+            name = re.sub(r"\(.*", "", re.sub(r"rgrg::", "", r[hdr.index("Kernel Name")])).replace("void ", "")[:120]
+            if any(s_ in name for s_ in skip):
+                continue
+            cells = []
+            for w, _ in WANT2:
+                if w not in hdr:
+                    cells.append("-")
+                    continue
+                i = hdr.index(w)
+                v, u = r[i], units[i]
+                try:
+                    v = "%.4g" % float(v.replace(",", ""))
+                except ValueError:
+                    pass
+                u = {"register/thread": "", "": "", "%": " %"}.get(u, " " + u)
+                cells.append(v + u)
+            f.write("| `%s` | " % name + " | ".join(cells) + " |\n")
+
+
 if __name__ == "__main__":
     kind = sys.argv[1]
-    (launch_list if kind == "list" else full_report)(*sys.argv[2:6])
+    if kind == "wide":
+        wide_table(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5], tuple(sys.argv[6:]))
+    else:
+        (launch_list if kind == "list" else full_report)(*sys.argv[2:6])
