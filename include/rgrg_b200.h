@@ -148,7 +148,8 @@ RGRG_API int rgrg_roi_tail(rgrg_engine_t* e, const float* class_logits_dev, cons
 
 /* D[M,N] (fp32 dev) = A[M,K] (bf16 dev) * W[N,K]^T (bf16 dev) + bias[N] (fp32 dev or NULL).
  * impl: 0 / 1 / 3 / 4 = tcgen05 with N tile 128 / 64 / 192 / 256, 5 = tcgen05 with the engine's own tile choice,
- *       2 = CUDA-core cross-check, 6 = the decoder's split-K form (4 K slices -> fp32 partial sums -> reduce, act must be 0).
+ *       2 = CUDA-core cross-check, 6 = the decoder's split-K form (4 K slices -> fp32 partial sums -> reduce, act must be 0),
+ *       7 / 8 = the CTA-pair kernel (tcgen05.mma.cta_group::2, N must be a multiple of 256): plain / split-K.
  *       act: 0 none, 1 relu, 2 gelu_new. */
 RGRG_API int rgrg_gemm_bf16(rgrg_engine_t* e, const void* A_dev, const void* W_dev, const float* bias_dev, int M, int N, int K,
                    int act, int impl, float* out_dev, void* stream);
@@ -175,6 +176,8 @@ RGRG_API int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst,
  *   "pdl" (0/1)               programmatic dependent launch between the kernels of a decode step
  *   "fused_attn" (0/1)        greedy decode: c_attn + KV append + attention as one head-aligned kernel (attn_fused.cuh);
  *                             0 = c_attn GEMM (KV-append epilogue) + stand-alone attention kernel (always used by beam search)
+ *   "gemm_2cta" (0/1)         decode projections through the CTA-pair kernel (256 x 256 tiles, each CTA stages half of W)
+ *   "dual" (0/1)              greedy decode step as two row halves half a layer out of phase (measured slower)
  *   "ln_head" (0/1)           LayerNorm (+ split-K reduce + residual) as the 16-CTA-cluster head of the consumer GEMM;
  *                             0 = separate LayerNorm kernels
  *   "attn_slots" (3/4/5)      fused attention: K/V ring slots per warp;  "l2_ahead" (n): items prefetched into L2

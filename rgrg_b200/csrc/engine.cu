@@ -22,6 +22,7 @@
 #include "detector_kernels.cuh"
 #include "epilogues.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_2cta.cuh"
 #include "gemm_tc.cuh"
 
 using namespace rgrg;
@@ -231,6 +232,8 @@ struct rgrg_engine {
   int opt_detector_precise = 0;  // fp32 detector (parity mode, see run_detect)
   int opt_fused_attn = 1;  // greedy decode: c_attn + KV append + attention as ONE head-aligned kernel (attn_fused.cuh)
   int opt_ln_head = 0;     // LayerNorm (+ split-K reduce + residual) as the cluster-cooperative head of the consumer GEMM
+  int opt_gemm_2cta = 1;        // decode projections (c_proj / c_fc / mlp c_proj) through the CTA-pair kernel (gemm_2cta.cuh)
+  int opt_dual = 0;             // greedy decode step as two row halves half a layer out of phase (decode_forward_dual)
   int opt_roi_align_sep = 1;    // RoIAlign in separable form (vertical interpolation once per feature column of a bin row)
   int opt_beam_fused_head = 1;  // beam search: log-softmax + per-part top-k fused into the lm_head epilogue (0: fp32 logits in HBM)
   int opt_attn_alg = 1;     // fused attention inner loop: 1 = order of dec::attention_dev (bit-identical to the two-kernel path), 2 = lane-per-key
@@ -241,6 +244,7 @@ struct rgrg_engine {
   int opt_attn_occ = 7;    // CTAs per SM the stand-alone attention kernel is compiled for (5: 88 regs, 6: 78, 7: 72, 8: 64)
   int opt_ablate = 0;  // tuning only: bit mask of decode-step kernels to skip (results become meaningless, timing attributes cost)
   bool pdl_now = false;  // set while the decode step is being issued: its kernels carry the PDL launch attribute
+  bool use_2cta_now = false;  // set while the decode projections are issued (and by the GEMM test entry): CTA-pair tiles
   std::unordered_map<std::string, HostRef> host;
   std::vector<void*> weight_allocs;
 
@@ -280,6 +284,11 @@ struct rgrg_engine {
     for (auto& g : step_graphs) cudaGraphExecDestroy(g.second);
     for (cudaEvent_t ev : prof_pool) cudaEventDestroy(ev);
     if (ev_enter) cudaEventDestroy(ev_enter);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    for (cudaEvent_t ev : ev_a) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ev_b) cudaEventDestroy(ev);
+    if (side_stream) cudaStreamDestroy(side_stream);
     if (own_stream) cudaStreamDestroy(own_stream);
     for (void* p : weight_allocs) cudaFree(p);
     for (auto& kv : preproc_tabs) kv.second.buf.release();
@@ -324,6 +333,20 @@ struct rgrg_engine {
     }
     if (W.K % 64 != 0) throw std::runtime_error("GEMM K must be a multiple of 64");
     const int mt = ceil_div(M, tc::BM);
+    if constexpr (!Epi::kDirect) {
+      if (use_2cta_now && W.N % tc2::BN == 0) {  // decode projections: CTA pairs on 256 x 256 tiles (gemm_2cta.cuh)
+        tc2::Shape s2{};
+        s2.M = M;
+        s2.N = W.N;
+        s2.k_iters = W.K / 64;
+        s2.m_pairs = ceil_div(mt, 2);
+        s2.n_tiles = W.N / tc2::BN;
+        CUtensorMap tmA2 = tc::make_tmap_2d(A, M, W.K, 128);
+        tc2::launch<Epi>(tmA2, W.tm[1], s2, epi, st, pdl_now);
+        ++launches;
+        return;
+      }
+    }
     const int bn = force_bn ? force_bn : pick_bn(mt, W.N);
     tc::GemmShape s{};
     s.M = M;
@@ -350,6 +373,20 @@ struct rgrg_engine {
       ++launches;
       return;
     }
+    if ((W.K / 64) % splits) throw std::runtime_error("split-K factor must divide K / 64");
+    if (use_2cta_now && W.N % tc2::BN == 0) {
+      tc2::Shape s2{};
+      s2.M = M;
+      s2.N = W.N;
+      s2.k_iters = W.K / 64;
+      s2.k_splits = splits;
+      s2.m_pairs = ceil_div(ceil_div(M, tc::BM), 2);
+      s2.n_tiles = W.N / tc2::BN;
+      CUtensorMap tmA2 = tc::make_tmap_2d(A, M, W.K, 128);
+      tc2::launch<decltype(ep)>(tmA2, W.tm[1], s2, ep, st, pdl_now);
+      ++launches;
+      return;
+    }
     tc::GemmShape s{};
     s.M = M;
     s.N = W.N;
@@ -358,7 +395,6 @@ struct rgrg_engine {
     s.m_tiles = ceil_div(M, tc::BM);
     s.n_tiles = ceil_div(W.N, 256);
     s.m_fastest = 1;
-    if (s.k_iters % splits) throw std::runtime_error("split-K factor must divide K / 64");
     CUtensorMap tmA = tc::make_tmap_2d(A, M, W.K, 128);
     launch_bn(256, tmA, W, s, ep, st);
     ++launches;
@@ -1241,117 +1277,206 @@ struct rgrg_engine {
     }
   }
 
-  // Transformer body of one decode step for `rows` rows (embedding .. final LayerNorm); every kernel reads the step index
-  // from device memory, so a captured CUDA graph of the step is replayed for every t.  Leaves ln_f(h) as bf16 in x.
+  // ---- transformer body of one decode step (embedding .. final LayerNorm) for a contiguous row range ("view").  Every
+  // kernel reads the step index from device memory, so a captured CUDA graph of the step is replayed for every t.
   //
-  // Greedy path, per layer (4 kernels): [LN1 head + c_attn + KV append + attention] -> attn c_proj (split-K) ->
-  // [LN2 head + c_fc + gelu_new] -> mlp c_proj (split-K).  The two bracketed kernels run as clusters of 16 CTAs (one M
-  // tile) whose LayerNorm head also folds the preceding projection's partial sums + bias into the residual stream.
-  // Beam search (cache rows are gathered through the ancestry table) and the cross-check GEMM keep the 7-kernel form:
-  // LN1, c_attn (KV-append epilogue), attention, c_proj, LN2, c_fc, c_proj.
-  void decode_forward(int rows, const int* ids_ptr, int ids_ld, cudaStream_t st) {
-    const int* sp = step.as<int>();
-    {
-      ProfScope ps(this, "embed", st);
-      launch_kernel(dec::embed_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, st, false, wte_f32, ids_ptr, ids_ld, sp, h.as<float>(), rows);
-      ++launches;
-    }
-    pdl_now = opt_pdl != 0;
-    constexpr int SPLITS = 4;
-    const size_t pstride = static_cast<size_t>(rows) * DM;
-    float* parts = splitk_parts.as<float>();
-    float* hp = h.as<float>();
-    bf16* xp = x.as<bf16>();
-    const bool tensor_path = opt_gemm_impl != 2;
-    const bool use_fused = opt_fused_attn && !beam_anc && tensor_path;
-    const bool use_head = opt_ln_head && tensor_path && ceil_div(rows, tc::BM) <= 512;
-    // LayerNorm fused with the residual update of the preceding split-K projection (pending_bias != null)
-    const float* pending_bias = nullptr;
-    auto ln = [&](const float* g, const float* b) {
-      ProfScope ps(this, "layernorm", st);
-      if (opt_ablate & 2) {
-        pending_bias = nullptr;
-        return;
-      }
-      if (pending_bias)
-        launch_kernel(dec::layernorm_kernel<SPLITS>, dim3(rows), dim3(128), 0, st, pdl_now, hp, g, b, xp, rows, parts, pstride, pending_bias);
+  // Greedy path, per layer: [c_attn + KV append + attention] (attn_fused.cuh) -> attn c_proj (split-K) -> LayerNorm ->
+  // c_fc + gelu_new -> mlp c_proj (split-K) -> LayerNorm; the LayerNorm kernels also fold the preceding projection's
+  // partial sums + bias into the residual stream.  Optional "ln_head": the LayerNorm runs as the head of its consumer
+  // kernel instead (measured slower, profiles/r02_decode.md).  Beam search (cache rows are gathered through the ancestry
+  // table) and the cross-check GEMM use c_attn (KV-append epilogue) + the stand-alone attention kernel.
+  struct DecView {
+    int row0, rows;
+    float* h;
+    bf16 *x, *q, *attn_o, *mid;
+    float* parts;
+    size_t pstride;
+    KvGeom kv;
+    const int* ids;  // first row of the view
+    int ids_ld;
+    unsigned* counters;  // LayerNorm-head counters of this view
+    CUtensorMap tm_x;
+    const float* pending_bias;  // bias of the split-K projection whose partial sums wait in `parts`
+  };
+  DecView dec_view(int row0, int rows, const int* ids_all, int ids_ld) {
+    DecView v{};
+    v.row0 = row0;
+    v.rows = rows;
+    v.h = h.as<float>() + static_cast<size_t>(row0) * DM;
+    v.x = x.as<bf16>() + static_cast<size_t>(row0) * DM;
+    v.q = q.as<bf16>() + static_cast<size_t>(row0) * DM;
+    v.attn_o = attn_o.as<bf16>() + static_cast<size_t>(row0) * DM;
+    v.mid = mlp_mid.as<bf16>() + static_cast<size_t>(row0) * 4 * DM;
+    v.parts = splitk_parts.as<float>() + static_cast<size_t>(row0) * DM * 4;  // each view keeps its 4 slices contiguous
+    v.pstride = static_cast<size_t>(rows) * DM;
+    v.kv = kv_geom();
+    v.kv.cache += static_cast<size_t>(row0) * 16 * ws_slots * 64;  // KvGeom::offset is linear in the row index
+    v.ids = ids_all + static_cast<size_t>(row0) * ids_ld;
+    v.ids_ld = ids_ld;
+    v.counters = ln_counters.as<unsigned>() + (row0 ? 256 : 0);
+    v.tm_x = tc::make_tmap_2d(v.x, rows, DM, 128);
+    v.pending_bias = nullptr;
+    return v;
+  }
+  bool decode_tensor_path() const { return opt_gemm_impl != 2; }
+  bool decode_use_fused() const { return opt_fused_attn && !beam_anc && decode_tensor_path(); }
+  bool decode_use_head(const DecView& v) const { return opt_ln_head && decode_tensor_path() && ceil_div(v.rows, tc::BM) <= 128; }
+
+  void view_embed(DecView& v, cudaStream_t st) {
+    ProfScope ps(this, "embed", st);
+    launch_kernel(dec::embed_kernel, dim3(ceil_div(v.rows, 8)), dim3(256), 0, st, false, wte_f32, v.ids, v.ids_ld, step.as<int>(), v.h, v.rows);
+    ++launches;
+  }
+  // LayerNorm fused with the residual update of the preceding split-K projection (pending_bias != null)
+  void view_ln(DecView& v, const float* g, const float* b, cudaStream_t st) {
+    ProfScope ps(this, "layernorm", st);
+    if (!(opt_ablate & 2)) {
+      if (v.pending_bias)
+        launch_kernel(dec::layernorm_kernel<4>, dim3(v.rows), dim3(128), 0, st, pdl_now, v.h, g, b, v.x, v.rows, v.parts, v.pstride, v.pending_bias);
       else
-        launch_kernel(dec::layernorm_kernel<0>, dim3(rows), dim3(128), 0, st, pdl_now, hp, g, b, xp, rows, parts, pstride, pending_bias);
+        launch_kernel(dec::layernorm_kernel<0>, dim3(v.rows), dim3(128), 0, st, pdl_now, v.h, g, b, v.x, v.rows, v.parts, v.pstride, v.pending_bias);
       ++launches;
-      pending_bias = nullptr;
-    };
-    CUtensorMap tm_x{};
-    if (use_fused) tm_x = tc::make_tmap_2d(xp, rows, DM, 128);
-    for (int l = 0; l < NLAYER; ++l) {
-      const LayerW& L = layers[l];
-      // ---- LN1 + c_attn + attention
-      if (use_fused) {
-        fa::Params fp{};
-        fp.bias = L.attn.bias;
-        fp.kv = kv_geom();
-        fp.layer = l;
-        fp.step_ptr = sp;
-        fp.attn_o = attn_o.as<bf16>();
-        fp.M = rows;
-        fp.l2_ahead = opt_l2_ahead;
-        if (use_head) {
-          fp.h = hp;
-          fp.x = xp;
-          fp.gamma = L.ln1_g;
-          fp.beta = L.ln1_b;
-          fp.parts = pending_bias ? parts : nullptr;
-          fp.part_stride = pstride;
-          fp.res_bias = pending_bias;
-          fp.counters = ln_counters.as<unsigned>();  // first half: the attention kernels' counters
-          fp.launch_idx = l;
-          fp.launches_per_step = NLAYER;
-          pending_bias = nullptr;
-        } else {
-          ln(L.ln1_g, L.ln1_b);
-        }
-        if (!(opt_ablate & 64)) {
-          ProfScope ps(this, "attn_fused", st);
-          if (use_head) launch_attn_fused<true>(tm_x, L.attn.tm[0], fp, st);
-          else launch_attn_fused<false>(tm_x, L.attn.tm[0], fp, st);
-          ++launches;
-        }
-      } else {
-        ln(L.ln1_g, L.ln1_b);
-        EpiQkvAppend eq{q.as<bf16>(), L.attn.bias, kv_geom(), l, sp};
-        if (!(opt_ablate & 4)) gemm("c_attn", xp, rows, L.attn, eq, st, true, opt_cattn_bn);
-        if (!(opt_ablate & 1)) {
-          ProfScope ps(this, "attention", st);
-          const dim3 grid(ceil_div(rows * 16, 4));
-          auto go = [&](auto kern) {
-            launch_kernel(kern, grid, dim3(128), 0, st, pdl_now, q.as<bf16>(), kv_geom(), l, sp, attn_o.as<bf16>(), rows, beam_anc,
-                          beam_slots, beam_nb);
-          };
-          if (opt_attn_occ == 6) go(dec::attention_kernel<6>);
-          else if (opt_attn_occ == 5) go(dec::attention_kernel<5>);
-          else if (opt_attn_occ == 8) go(dec::attention_kernel<8>);
-          else go(dec::attention_kernel<7>);
-          ++launches;
-        }
-      }
-      // ---- attention c_proj: split-K partial sums, reduced (+ bias, + residual) by the LayerNorm that follows
-      if (!(opt_ablate & 8)) gemm_splitk("attn_c_proj", attn_o.as<bf16>(), rows, L.proj, parts, SPLITS, st);
-      pending_bias = L.proj.bias;
-      // ---- LN2 + c_fc + gelu_new
-      auto ep_fc = epi<true, ACT_GELU_NEW, RES_NONE, true>(mlp_mid.p, L.fc.bias, 4 * DM);
-      if (use_head) {
-        tc::GemmShape::LnHead lh{hp, xp, L.ln2_g, L.ln2_b, parts, pstride, pending_bias, ln_counters.as<unsigned>() + 512, sp,
-                                 l, NLAYER};  // second half of the counter array: the c_fc kernels' counters
-        pending_bias = nullptr;
-        if (!(opt_ablate & 16)) gemm_ln_head("mlp_c_fc", xp, rows, L.fc, ep_fc, lh, st);
-      } else {
-        ln(L.ln2_g, L.ln2_b);
-        if (!(opt_ablate & 16)) gemm("mlp_c_fc", xp, rows, L.fc, ep_fc, st, true);
-      }
-      // ---- mlp c_proj
-      if (!(opt_ablate & 32)) gemm_splitk("mlp_c_proj", mlp_mid.as<bf16>(), rows, L.mproj, parts, SPLITS, st);
-      pending_bias = L.mproj.bias;
     }
-    ln(lnf_g, lnf_b);
+    v.pending_bias = nullptr;
+  }
+  // LN1 + c_attn + KV append + attention of layer l; `before_attn` runs right before the attention kernel is launched
+  // (the two-halves schedule hangs its cross-stream dependency there)
+  template <class F>
+  void view_attn(DecView& v, int l, cudaStream_t st, F&& before_attn) {
+    const LayerW& L = layers[l];
+    const int* sp = step.as<int>();
+    if (decode_use_fused()) {
+      const bool head = decode_use_head(v);
+      fa::Params fp{};
+      fp.bias = L.attn.bias;
+      fp.kv = v.kv;
+      fp.layer = l;
+      fp.step_ptr = sp;
+      fp.attn_o = v.attn_o;
+      fp.M = v.rows;
+      fp.l2_ahead = opt_l2_ahead;
+      if (head) {
+        fp.h = v.h;
+        fp.x = v.x;
+        fp.gamma = L.ln1_g;
+        fp.beta = L.ln1_b;
+        fp.parts = v.pending_bias ? v.parts : nullptr;
+        fp.part_stride = v.pstride;
+        fp.res_bias = v.pending_bias;
+        fp.counters = v.counters;  // first half of the view's counters: the attention kernels
+        fp.launch_idx = l;
+        fp.launches_per_step = NLAYER;
+        v.pending_bias = nullptr;
+      } else {
+        view_ln(v, L.ln1_g, L.ln1_b, st);
+      }
+      before_attn();
+      if (!(opt_ablate & 64)) {
+        ProfScope ps(this, "attn_fused", st);
+        if (head) launch_attn_fused<true>(v.tm_x, L.attn.tm[0], fp, st);
+        else launch_attn_fused<false>(v.tm_x, L.attn.tm[0], fp, st);
+        ++launches;
+      }
+    } else {
+      view_ln(v, L.ln1_g, L.ln1_b, st);
+      EpiQkvAppend eq{v.q, L.attn.bias, v.kv, l, sp};
+      if (!(opt_ablate & 4)) gemm("c_attn", v.x, v.rows, L.attn, eq, st, true, opt_cattn_bn);
+      before_attn();
+      if (!(opt_ablate & 1)) {
+        ProfScope ps(this, "attention", st);
+        const dim3 grid(ceil_div(v.rows * 16, 4));
+        const unsigned char* anc = beam_anc ? beam_anc + static_cast<size_t>(v.row0) * beam_slots : nullptr;
+        auto go = [&](auto kern) {
+          launch_kernel(kern, grid, dim3(128), 0, st, pdl_now, v.q, v.kv, l, sp, v.attn_o, v.rows, anc, beam_slots, beam_nb);
+        };
+        if (opt_attn_occ == 6) go(dec::attention_kernel<6>);
+        else if (opt_attn_occ == 5) go(dec::attention_kernel<5>);
+        else if (opt_attn_occ == 8) go(dec::attention_kernel<8>);
+        else go(dec::attention_kernel<7>);
+        ++launches;
+      }
+    }
+  }
+  // attn c_proj (split-K) -> LN2 -> c_fc + gelu_new -> mlp c_proj (split-K) of layer l
+  void view_mlp(DecView& v, int l, cudaStream_t st) {
+    const LayerW& L = layers[l];
+    constexpr int SPLITS = 4;
+    use_2cta_now = opt_gemm_2cta && decode_tensor_path();
+    struct Reset {
+      bool& f;
+      ~Reset() { f = false; }
+    } reset{use_2cta_now};
+    if (!(opt_ablate & 8)) gemm_splitk("attn_c_proj", v.attn_o, v.rows, L.proj, v.parts, SPLITS, st);
+    v.pending_bias = L.proj.bias;
+    auto ep_fc = epi<true, ACT_GELU_NEW, RES_NONE, true>(v.mid, L.fc.bias, 4 * DM);
+    if (decode_use_head(v)) {
+      tc::GemmShape::LnHead lh{v.h, v.x, L.ln2_g, L.ln2_b, v.parts, v.pstride, v.pending_bias, v.counters + 128, step.as<int>(),
+                               l, NLAYER};  // second half of the view's counters: the c_fc kernels
+      v.pending_bias = nullptr;
+      if (!(opt_ablate & 16)) gemm_ln_head("mlp_c_fc", v.x, v.rows, L.fc, ep_fc, lh, st);
+    } else {
+      view_ln(v, L.ln2_g, L.ln2_b, st);
+      if (!(opt_ablate & 16)) gemm("mlp_c_fc", v.x, v.rows, L.fc, ep_fc, st, true);
+    }
+    if (!(opt_ablate & 32)) gemm_splitk("mlp_c_proj", v.mid, v.rows, L.mproj, v.parts, SPLITS, st);
+    v.pending_bias = L.mproj.bias;
+  }
+
+  // one chain over all rows; leaves ln_f(h) as bf16 in x
+  void decode_forward(int rows, const int* ids_ptr, int ids_ld, cudaStream_t st) {
+    DecView v = dec_view(0, rows, ids_ptr, ids_ld);
+    view_embed(v, st);
+    pdl_now = opt_pdl != 0;
+    for (int l = 0; l < NLAYER; ++l) {
+      view_attn(v, l, st, [] {});
+      view_mlp(v, l, st);
+    }
+    view_ln(v, lnf_g, lnf_b, st);
+  }
+
+  // The same as TWO row halves on two streams (inside the step graph: two branches).  Rows never interact.  The halves are
+  // kept half a layer out of phase by cross-stream dependencies — half B's attention kernel of layer l starts when half
+  // A's has finished, half A's of layer l+1 when half B's of layer l has — so that while one half streams its KV cache
+  // (HBM-bound, 64 CTAs) the other half runs its GEMM / LayerNorm kernels (L2- and tensor-bound, 64 CTAs) on the other SMs:
+  // the fused attention kernel and the decode GEMMs each take one SM per CTA, so half-size launches co-reside.
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  std::vector<cudaEvent_t> ev_a, ev_b;
+  void decode_forward_dual(int rows, const int* ids_ptr, int ids_ld, cudaStream_t st) {
+    if (!side_stream) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+      ev_a.resize(NLAYER);
+      ev_b.resize(NLAYER);
+      for (int l = 0; l < NLAYER; ++l) {
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_a[l], cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_b[l], cudaEventDisableTiming));
+      }
+    }
+    int rows_a = ((rows / 2 + tc::BM - 1) / tc::BM) * tc::BM;  // split on an M-tile boundary: no extra tile padding
+    if (rows_a >= rows) rows_a = rows / 2;
+    DecView va = dec_view(0, rows_a, ids_ptr, ids_ld), vb = dec_view(rows_a, rows - rows_a, ids_ptr, ids_ld);
+    cudaStream_t sa = st, sb = side_stream;
+    CUDA_CHECK(cudaEventRecord(ev_fork, sa));
+    CUDA_CHECK(cudaStreamWaitEvent(sb, ev_fork, 0));
+    view_embed(va, sa);
+    view_embed(vb, sb);
+    pdl_now = opt_pdl != 0;
+    for (int l = 0; l < NLAYER; ++l) {
+      view_attn(va, l, sa, [&] {
+        if (l > 0) CUDA_CHECK(cudaStreamWaitEvent(sa, ev_b[l - 1], 0));
+      });
+      CUDA_CHECK(cudaEventRecord(ev_a[l], sa));
+      view_attn(vb, l, sb, [&] { CUDA_CHECK(cudaStreamWaitEvent(sb, ev_a[l], 0)); });
+      CUDA_CHECK(cudaEventRecord(ev_b[l], sb));
+      view_mlp(va, l, sa);
+      view_mlp(vb, l, sb);
+    }
+    view_ln(va, lnf_g, lnf_b, sa);
+    view_ln(vb, lnf_g, lnf_b, sb);
+    CUDA_CHECK(cudaEventRecord(ev_join, sb));
+    CUDA_CHECK(cudaStreamWaitEvent(sa, ev_join, 0));
   }
   void end_pdl() { pdl_now = false; }
 
@@ -1380,7 +1505,8 @@ struct rgrg_engine {
   // one greedy decode step over all rows
   int decode_step(int rows, const dec::GreedyState& g, float* logits_out, cudaStream_t st) {
     const int before = static_cast<int>(launches);
-    decode_forward(rows, g.ids, g.ids_ld, st);
+    if (opt_dual && rows >= 2 * tc::BM && decode_use_fused() && !prof_on) decode_forward_dual(rows, g.ids, g.ids_ld, st);
+    else decode_forward(rows, g.ids, g.ids_ld, st);
     decode_head(rows, g, logits_out, st);
     return static_cast<int>(launches) - before;
   }
@@ -1854,6 +1980,8 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "attn_alg") e->opt_attn_alg = value;
   else if (k == "beam_fused_head") e->opt_beam_fused_head = value;
   else if (k == "roi_align_sep") e->opt_roi_align_sep = value;
+  else if (k == "dual") e->opt_dual = value;
+  else if (k == "gemm_2cta") e->opt_gemm_2cta = value;
   else if (k == "l2_ahead") e->opt_l2_ahead = value;
   else if (k == "attn_occ") e->opt_attn_occ = value;
   else if (k == "cattn_bn") e->opt_cattn_bn = value;
@@ -2225,7 +2353,12 @@ int rgrg_gemm_bf16(rgrg_engine_t* e, const void* A_dev, const void* W_dev, const
     const bf16* A = static_cast<const bf16*>(A_dev);
     try {
       if (impl != 2) L.make_maps();
-      if (impl == 6) {  // the decoder's split-K form: 4 K slices -> fp32 partial sums, reduced (+ bias) afterwards
+      if (impl == 7 || impl == 8) e->use_2cta_now = true;  // CTA-pair kernel: plain (7) / split-K (8)
+      struct Reset2 {
+        bool& f;
+        ~Reset2() { f = false; }
+      } reset2{e->use_2cta_now};
+      if (impl == 6 || impl == 8) {  // the decoder's split-K form: 4 K slices -> fp32 partial sums, reduced (+ bias) afterwards
         if (act != ACT_NONE) throw std::runtime_error("split-K test path has no activation");
         DevBuf parts;
         parts.ensure(static_cast<size_t>(4) * M * N * 4);

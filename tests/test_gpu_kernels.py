@@ -60,6 +60,25 @@ def test_gemm_split_k_form(eng_bare, M, N, K):
     assert err <= 2e-3 * max(1.0, ref.abs().max().item()), "max abs err %g" % err
 
 
+@pytest.mark.parametrize("M,N,K", [(928, 4096, 1024), (928, 1024, 4096), (100, 256, 128), (300, 512, 320), (129, 1024, 1024), (1856, 4096, 1024)])
+def test_gemm_cta_pair_kernel(eng_bare, M, N, K):
+    """gemm_2cta.cuh (tcgen05.mma.cta_group::2, 256 x 256 pair-tiles, each CTA stages half of W): plain and split-K forms,
+    odd numbers of M tiles (the pair's second CTA past the end), short K."""
+    A = _rand_bf16((M, K), 31)
+    W = _rand_bf16((N, K), 32, 0.05)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(33)).cuda()
+    ref = A.float() @ W.float().T + bias
+    tol = 2e-3 * max(1.0, ref.abs().max().item())
+    out = eng_bare.gemm(A, W, bias, act=0, impl=7)
+    assert (out - ref).abs().max().item() <= tol
+    if (K // 64) % 4 == 0:
+        out = eng_bare.gemm(A, W, bias, act=0, impl=8)
+        assert (out - ref).abs().max().item() <= tol
+    out = eng_bare.gemm(A, W, bias, act=2, impl=7)
+    g = 0.5 * ref * (1 + torch.tanh(0.7978845608028654 * (ref + 0.044715 * ref ** 3)))
+    assert (out - g).abs().max().item() <= 2e-3 * max(1.0, g.abs().max().item())
+
+
 @pytest.mark.parametrize("act", [1, 2])
 def test_gemm_epilogue_activations(eng_bare, act):
     A = _rand_bf16((200, 128), 4)

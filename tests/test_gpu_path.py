@@ -303,6 +303,44 @@ def test_layernorm_head_matches_separate_layernorm(model, oracle_detail):
     assert np.array_equal(a[:, :4], b[:, :4]) and (a == b).mean() > 0.9
 
 
+def test_cta_pair_projections_are_bit_identical(model, oracle_detail):
+    """Decode projections through the CTA-pair kernel vs the 1-CTA kernel: same k order and fp32 accumulation, so tokens
+    are identical (full M tiles, a partial last tile, an odd tile count)."""
+    eng = model._engine()
+    feats = torch.cat([oracle_detail["sel_feats"]] * 7, 0).contiguous().cuda()  # 406 rows
+    try:
+        for rows in (406, 290, 60):
+            _opts(eng, gemm_2cta=0)
+            a = eng.lm_generate(feats[:rows], 16)
+            _opts(eng, gemm_2cta=1)
+            b = eng.lm_generate(feats[:rows], 16)
+            _opts(eng, cuda_graph=0)
+            c = eng.lm_generate(feats[:rows], 16)
+            _opts(eng, cuda_graph=1)
+            assert np.array_equal(a, b) and np.array_equal(a, c), rows
+    finally:
+        _opts(eng, gemm_2cta=1, cuda_graph=1)
+
+
+def test_two_halves_schedule_is_bit_identical_to_single_chain(model, oracle_detail):
+    """decode_forward_dual: two row halves on two streams, half a layer out of phase (cross-stream dependencies per layer).
+    Rows never interact and the split is on an M-tile boundary, so tokens are IDENTICAL to the single chain — under graph
+    replay and eagerly, with an even and an uneven split."""
+    eng = model._engine()
+    feats = torch.cat([oracle_detail["sel_feats"]] * 8, 0).contiguous().cuda()  # 464 rows
+    try:
+        for rows in (464, 300, 256):
+            _opts(eng, dual=0, cuda_graph=1)
+            a = eng.lm_generate(feats[:rows], 20)
+            _opts(eng, dual=1)
+            b = eng.lm_generate(feats[:rows], 20)
+            _opts(eng, cuda_graph=0)
+            c = eng.lm_generate(feats[:rows], 20)
+            assert np.array_equal(a, b) and np.array_equal(a, c), rows
+    finally:
+        _opts(eng, dual=0, cuda_graph=1)
+
+
 def test_padded_row_count_does_not_change_rows(model, oracle_detail):
     """The decoder runs on round_up(R, 32) rows (one step graph per padded size): a row's tokens do not depend on how
     many rows share the batch."""

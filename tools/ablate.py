@@ -34,7 +34,12 @@ import numpy as np
 print("max active 16-CTA clusters:", int(eng.debug_read("cluster16_max_active", (1,), np.int32)[0]), flush=True)
 eng.set_option("ln_head", 0)
 base = run(0)
-print("full step (fused attention, separate LayerNorm): %.3f ms" % base, flush=True)
+print("full step (fused attention, CTA-pair projections): %.3f ms" % base, flush=True)
+print("  gemm_2cta=0                       : %.3f ms" % run(0, gemm_2cta=0), flush=True)
+eng.set_option("gemm_2cta", 1)
+if "variants" in sys.argv:
+    print("  dual=1 (two halves out of phase)  : %.3f ms" % run(0, dual=1), flush=True)
+    eng.set_option("dual", 0)
 if "variants" in sys.argv:
     for alg, aw, sl in ((2, 16, 2), (1, 16, 2)):
         print("  attn_alg=%d attn_warps=%d attn_slots=%d : %.3f ms" % (alg, aw, sl, run(0, attn_alg=alg, attn_warps=aw, attn_slots=sl)), flush=True)
