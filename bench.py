@@ -462,7 +462,7 @@ def main():
             achieved = fl / (avg_ms / 1e3) / 1e12
             peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
             roofline = {"kernel": top, "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                        "frac": achieved / peak, "traffic": (ncu_traffic(top) or {}).get("bytes_per_launch"),
+                        "frac": achieved / peak, "traffic": None,
                         "peak_source": peaks["_source"] + " (sustained bf16 GEMM)",
                         "launches": n, "avg_ms": avg_ms, "timing": timing}
         else:
@@ -470,7 +470,8 @@ def main():
             if by is not None:
                 achieved = by / (avg_ms / 1e3) / 1e9
                 roofline = {"kernel": top, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                            "frac": achieved / peaks["hbm_gbs"], "traffic": (ncu_traffic(top) or {}).get("bytes_per_launch"),
+                            "frac": achieved / peaks["hbm_gbs"],
+                            "traffic": (by * ncu_traffic(top)["ratio"]) if (ncu_traffic(top) or {}).get("ratio") else None,
                             "traffic_note": (ncu_traffic(top) or {}).get("note"), "peak_source": peaks["_source"],
                             "launches": n, "avg_ms": avg_ms, "timing": timing, "algorithmic_bytes_per_launch": by,
                             "note": "algorithmic bytes per launch = rows x (mean L - 1) x 4096 B cached K/V read + rows x 4096 B "

@@ -9,7 +9,8 @@ GPU box.  This file is used
     the oracle port and say so (`kind: "port"`).
 The `-m gpu` tests and smoke() never import it.
 
-Two stubs + two patches; no reference file is edited or copied:
+Two stubs + two patches, plus `torch.cuda.is_available() -> False` while the reference is imported and
+built (it picks its device at import time; the CPU legs must stay on the CPU on a GPU box); no reference file is edited:
   1. sys.modules['torchinfo']                         (language_model.py:6  `from torchinfo import summary`)
   2. sys.modules['transformers.generation_beam_search'] -> oracle BeamSearchScorer restatement
                                                       (language_model.py:8; transformers 4.19.2 is not installed)
@@ -38,6 +39,25 @@ REFERENCE_ROOT = _default_root()
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "full_model"))
+
+
+class _pin_to_cpu:
+    """The reference picks its device at import / construction time (`device = cuda if torch.cuda.is_available() else cpu`:
+    language_model.py:199, binary_classifier_region_selection.py:4, ...) while the harness keeps the model on the CPU; on a
+    box WITH a GPU that mixes devices inside greedy_search.  The CPU legs therefore import and build the reference with
+    torch.cuda.is_available() answering False (restored afterwards) — the reference files stay untouched."""
+
+    def __enter__(self):
+        import torch
+
+        self._saved = torch.cuda.is_available
+        torch.cuda.is_available = lambda: False
+
+    def __exit__(self, *exc):
+        import torch
+
+        torch.cuda.is_available = self._saved
+        return False
 
 
 def import_reference():
@@ -82,9 +102,10 @@ def import_reference():
 
 def build_reference_model(state_dict=None):
     import torch
-    RGM = import_reference()
-    torch.manual_seed(0)
-    model = RGM(pretrain_without_lm_model=True)
+    with _pin_to_cpu():
+        RGM = import_reference()
+        torch.manual_seed(0)
+        model = RGM(pretrain_without_lm_model=True)
     if state_dict is not None:
         missing, unexpected = model.load_state_dict(state_dict, strict=False)
         # the reference aliases the GPT-2 weights 3x; our synthetic state_dict carries every alias

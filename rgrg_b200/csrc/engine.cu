@@ -232,6 +232,7 @@ struct rgrg_engine {
   int opt_detector_precise = 0;  // fp32 detector (parity mode, see run_detect)
   int opt_fused_attn = 1;  // greedy decode: c_attn + KV append + attention as ONE head-aligned kernel (attn_fused.cuh)
   int opt_ln_head = 0;     // LayerNorm (+ split-K reduce + residual) as the cluster-cooperative head of the consumer GEMM
+  int opt_gemm_2cta_stages = 6; // its TMA ring depth: 6 (one CTA per SM) / 4 / 3 (two CTAs per SM: prologue overlaps the predecessor's epilogue)
   int opt_gemm_2cta = 1;        // decode projections (c_proj / c_fc / mlp c_proj) through the CTA-pair kernel (gemm_2cta.cuh)
   int opt_dual = 0;             // greedy decode step as two row halves half a layer out of phase (decode_forward_dual)
   int opt_roi_align_sep = 1;    // RoIAlign in separable form (vertical interpolation once per feature column of a bin row)
@@ -342,7 +343,9 @@ struct rgrg_engine {
         s2.m_pairs = ceil_div(mt, 2);
         s2.n_tiles = W.N / tc2::BN;
         CUtensorMap tmA2 = tc::make_tmap_2d(A, M, W.K, 128);
-        tc2::launch<Epi>(tmA2, W.tm[1], s2, epi, st, pdl_now);
+        if (opt_gemm_2cta_stages == 3) tc2::launch<Epi, 3>(tmA2, W.tm[1], s2, epi, st, pdl_now);
+        else if (opt_gemm_2cta_stages == 4) tc2::launch<Epi, 4>(tmA2, W.tm[1], s2, epi, st, pdl_now);
+        else tc2::launch<Epi, 6>(tmA2, W.tm[1], s2, epi, st, pdl_now);
         ++launches;
         return;
       }
@@ -383,7 +386,9 @@ struct rgrg_engine {
       s2.m_pairs = ceil_div(ceil_div(M, tc::BM), 2);
       s2.n_tiles = W.N / tc2::BN;
       CUtensorMap tmA2 = tc::make_tmap_2d(A, M, W.K, 128);
-      tc2::launch<decltype(ep)>(tmA2, W.tm[1], s2, ep, st, pdl_now);
+      if (opt_gemm_2cta_stages == 3) tc2::launch<decltype(ep), 3>(tmA2, W.tm[1], s2, ep, st, pdl_now);
+      else if (opt_gemm_2cta_stages == 4) tc2::launch<decltype(ep), 4>(tmA2, W.tm[1], s2, ep, st, pdl_now);
+      else tc2::launch<decltype(ep), 6>(tmA2, W.tm[1], s2, ep, st, pdl_now);
       ++launches;
       return;
     }
@@ -1982,6 +1987,7 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "roi_align_sep") e->opt_roi_align_sep = value;
   else if (k == "dual") e->opt_dual = value;
   else if (k == "gemm_2cta") e->opt_gemm_2cta = value;
+  else if (k == "gemm_2cta_stages") e->opt_gemm_2cta_stages = value;
   else if (k == "l2_ahead") e->opt_l2_ahead = value;
   else if (k == "attn_occ") e->opt_attn_occ = value;
   else if (k == "cattn_bn") e->opt_cattn_bn = value;
@@ -2419,7 +2425,7 @@ int rgrg_gemm_bench(rgrg_engine_t* e, int M, int N, int K, int bn, int iters, in
     s.N = N;
     s.k_iters = K / 64;
     s.m_tiles = ceil_div(M, 128);
-    s.n_tiles = ceil_div(N, bn);
+    s.n_tiles = ceil_div(N, bn == 512 ? 256 : bn);
     s.m_fastest = 1;
     CUtensorMap tmA = tc::make_tmap_2d(A.as<bf16>(), M, K, 128);
     cudaEvent_t a;
@@ -2430,7 +2436,17 @@ int rgrg_gemm_bench(rgrg_engine_t* e, int M, int N, int K, int bn, int iters, in
       if (rep == 1) CUDA_CHECK(cudaEventRecord(a, st));
       for (int i = 0; i < iters; ++i) {
         s.trace = (rep == 1 && i == iters - 1) ? T.as<long long>() : nullptr;
-        e->launch_bn(bn, tmA, L, s, ep, st);
+        if (bn == 512) {  // the CTA-pair kernel (256 x 256 pair-tiles)
+          tc2::Shape s2{};
+          s2.M = M;
+          s2.N = N;
+          s2.k_iters = K / 64;
+          s2.m_pairs = ceil_div(ceil_div(M, 128), 2);
+          s2.n_tiles = N / 256;
+          tc2::launch<decltype(ep), 6>(tmA, L.tm[1], s2, ep, st, false);
+        } else {
+          e->launch_bn(bn, tmA, L, s, ep, st);
+        }
         if (interleave)
           dec::layernorm_kernel<0><<<M, 128, 0, st>>>(H.as<float>(), G.as<float>(), G.as<float>(), A.as<bf16>(), M, nullptr, 0,
                                                                   nullptr);

@@ -20,14 +20,18 @@ namespace tc2 {
 
 constexpr int BN = 256;          // pair-tile N
 constexpr int HALF_N = BN / 2;   // W rows each CTA stages
-constexpr int STAGES = 6;
 constexpr int A_BYTES = tc::BM * tc::BK * 2;      // 16 KB
 constexpr int B_BYTES = HALF_N * tc::BK * 2;      // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // per CTA
-constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
 constexpr int STG_BYTES = tc::EPI_WARPS * tc::STG_FLOATS * 4;
-constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
-constexpr int SMEM_TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;
+// STAGES = 6: 209 KB, one CTA per SM.  STAGES = 3: 113 KB — two CTAs (2 x 256 TMEM columns) fit on an SM, so the
+// prologue of the next projection kernel overlaps the epilogue of the current one under PDL.
+template <int STAGES>
+struct Layout {
+  static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
 constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;       // clears the CTA-rank bit of a shared::cluster address: the leader's copy
 
 struct Shape {
@@ -72,11 +76,12 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                : "memory");
 }
 
-template <class Epi>
+template <class Epi, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NUM_THREADS, 1)
     gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Shape s, const Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int BAR_OFFSET = Layout<STAGES>::BAR_OFFSET, STG_OFFSET = Layout<STAGES>::STG_OFFSET;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
@@ -206,9 +211,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NUM_THREADS, 1)
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
 }
 
-template <class Epi>
+template <class Epi, int STAGES>
 inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Shape& s, const Epi& epi, cudaStream_t stream, bool pdl) {
-  auto kern = gemm_2cta_kernel<Epi>;
+  auto kern = gemm_2cta_kernel<Epi, STAGES>;
+  constexpr int SMEM_TOTAL = Layout<STAGES>::TOTAL;
   static bool configured = false;  // one engine device per process (rgrg_create enforces it)
   if (!configured) {
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));

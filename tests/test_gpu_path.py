@@ -247,6 +247,20 @@ def test_beam_fused_head_matches_logits_path(model, oracle_detail):
         assert np.array_equal(a[:, :3], b[:, :3]) and (a == b).mean() > 0.9, nb
 
 
+def test_out_of_memory_is_recoverable(model, oracle_detail):
+    """the reference's callers catch "out of memory" and carry on with the next batch
+    (evaluate_language_model.py:1207-1222).  A KV cache that cannot be allocated (4096 rows x 1024 tokens = 412 GB) must raise
+    a RuntimeError carrying that substring and leave the engine usable: workspace growth is transactional."""
+    eng = model._engine()
+    feats = oracle_detail["sel_feats"][:8].contiguous().cuda()
+    ref = eng.lm_generate(feats, 6)
+    big = torch.zeros(4096, 1024, device="cuda")
+    with pytest.raises(RuntimeError, match="out of memory"):
+        eng.lm_generate(big, 1024)
+    assert np.array_equal(eng.lm_generate(feats, 6), ref)          # same small batch: workspace rebuilt from scratch
+    assert eng.lm_generate(feats[:3], 9).shape == (3, 9)
+
+
 def _opts(eng, **kw):
     for k, v in kw.items():
         eng.set_option(k, v)

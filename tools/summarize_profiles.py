@@ -66,7 +66,10 @@ WANT2 = [("gpu__time_duration.sum", "duration"), ("launch__grid_size", "grid"), 
 
 def wide_table(rep_path, out_path, title, note, skip=()):
     """one row per captured launch, one column per metric"""
-    out = subprocess.run(["ncu", "-i", rep_path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep_path.endswith(".csv"):  # already exported on the GPU box: `ncu -i rep --page raw --csv`
+        out = open(rep_path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep_path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     with open(out_path, "w") as f:
