@@ -68,6 +68,8 @@ struct Params {
   const int* step_ptr;   // device-side decode step t (word t is cached at slot t + 1)
   bf16* attn_o;          // [M, 1024]
   int M;
+  int rows_per_tile;     // rows OWNED by one M tile (<= 128; the MMA still covers 128 rows, the surplus belongs to the next tile):
+                         // rows are spread evenly over as many tiles as there are SMs / 16, so every CTA streams the same amount
   int l2_ahead;          // items whose K / V blocks are prefetched into L2 ahead of the consumer (0 = off; measured: no gain —
                          // neither this nor prefetching the NEXT layer's cache during the GEMM kernels, profiles/r02_decode.md)
   // optional LayerNorm head (null h = off; needs a 16-CTA cluster launch)
@@ -105,7 +107,7 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 //           per key (4 bytes per lane), all 32 of a chunk issued before the q.K^T math; p[key] is broadcast by shuffle.
 // ---------------------------------------------------------------------------------------------------------------
 template <int AW, int NSLOT>
-__device__ __forceinline__ void attention_v2(uint8_t* smem, uint64_t* att_bar, const Params& p, int aw, int lane, int head, int m_blk,
+__device__ __forceinline__ void attention_v2(uint8_t* smem, uint64_t* att_bar, const Params& p, int aw, int lane, int head, int row0,
                                              int n_items, int t) {
   using L = Smem<AW, NSLOT, 2>;
   constexpr int CK = 32;  // keys per chunk
@@ -116,7 +118,7 @@ __device__ __forceinline__ void attention_v2(uint8_t* smem, uint64_t* att_bar, c
   float* qs = reinterpret_cast<float*>(smem + L::Q_OFFSET + aw * 256);
   uint64_t* bars = att_bar + aw * NSLOT;
   const int total = n_items * nsc;
-  auto item_row = [&](int j) { return m_blk * tc::BM + aw + AW * j; };
+  auto item_row = [&](int j) { return row0 + aw + AW * j; };
   auto issue = [&](int seq) {
     if (lane == 0) {
       const int j = seq / nsc, c = seq - j * nsc;
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
           for (int j = 0; j < 3; ++j)
             tc::tma_load_2d(a_dst + A_BYTES + j * 64 * 128, &tmW, &full_bar[st], kb * tc::BK, j * 1024 + head * 64);
         }
-        tc::tma_load_2d(a_dst, &tmA, &full_bar[st], kb * tc::BK, m_blk * tc::BM);
+        tc::tma_load_2d(a_dst, &tmA, &full_bar[st], kb * tc::BK, m_blk * p.rows_per_tile);
       }
     }
   } else if (warp == 1) {
@@ -310,13 +312,14 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
   } else {
     // ---------------------------------------------------------------- epilogue + attention (warps 2..9)
     const int aw = warp - 2;
-    const int rows_left = p.M - m_blk * tc::BM;  // valid rows of this M tile (>= 1)
+    const int row0 = m_blk * p.rows_per_tile;
+    const int rows_left = min(p.rows_per_tile, p.M - row0);  // rows this M tile owns (>= 1)
     // items of this warp: local rows aw, aw + AW, ... (a short last M tile still spreads over all warps)
-    const int n_items = rows_left > aw ? min((tc::BM - aw + AW - 1) / AW, (rows_left - aw + AW - 1) / AW) : 0;
+    const int n_items = rows_left > aw ? (rows_left - aw + AW - 1) / AW : 0;
     const int nsc = (Lc + CHUNK_KEYS - 1) / CHUNK_KEYS;       // staged chunks per item (cached keys)
     const int nchunks = (Ltot + CHUNK_KEYS - 1) / CHUNK_KEYS;  // compute chunks per item (cached + new key)
     const uint32_t blk_bytes = static_cast<uint32_t>(Lc) * 128;
-    auto item_row = [&](int j) { return m_blk * tc::BM + aw + AW * j; };
+    auto item_row = [&](int j) { return row0 + aw + AW * j; };
     if (p.l2_ahead > 0 && lane == 0) {
       for (int j = 0; j < p.l2_ahead && j < n_items; ++j) {
         bulk_prefetch_l2(p.kv.cache + p.kv.offset(p.layer, 0, item_row(j), head, 0), blk_bytes);
@@ -331,8 +334,8 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
       const int q4 = warp & 3;           // TMEM lane quarter this warp may read
       const int grp = aw >> 2;           // which of the AW / 4 warps of that quarter: takes 16-column chunks grp, grp + AW/4, ...
       const int r = q4 * 32 + lane;      // local row
-      const int row = m_blk * tc::BM + r;
-      const bool row_ok = row < p.M;
+      const int row = row0 + r;
+      const bool row_ok = r < rows_left;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
       const int slot = t + 1;
 #pragma unroll 1
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
     asm volatile("bar.sync 1, %0;" ::"r"(32 * AW) : "memory");  // all attention warps: tiles complete, the GEMM ring is free for staging
 
     if constexpr (ALG == 2) {
-      attention_v2<AW, NSLOT>(smem, att_bar, p, aw, lane, head, m_blk, n_items, t);
+      attention_v2<AW, NSLOT>(smem, att_bar, p, aw, lane, head, row0, n_items, t);
     } else {
       // ---- attention
       const int sub = lane >> 3, dseg = lane & 7;
@@ -488,7 +491,7 @@ inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const Params&
     configured = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(ceil_div(p.M, tc::BM) * 16);
+  cfg.gridDim = dim3(ceil_div(p.M, p.rows_per_tile) * 16);
   cfg.blockDim = dim3(64 + 32 * AW);
   cfg.dynamicSmemBytes = L::TOTAL;
   cfg.stream = stream;

@@ -232,6 +232,7 @@ struct rgrg_engine {
   int opt_detector_precise = 0;  // fp32 detector (parity mode, see run_detect)
   int opt_fused_attn = 1;  // greedy decode: c_attn + KV append + attention as ONE head-aligned kernel (attn_fused.cuh)
   int opt_ln_head = 0;     // LayerNorm (+ split-K reduce + residual) as the cluster-cooperative head of the consumer GEMM
+  int opt_attn_balance = 1;     // fused attention: rows spread evenly over (#SMs / 16) M tiles instead of 128-row tiles
   int opt_gemm_2cta_stages = 6; // its TMA ring depth: 6 (one CTA per SM) / 4 / 3 (two CTAs per SM: prologue overlaps the predecessor's epilogue)
   int opt_gemm_2cta = 1;        // decode projections (c_proj / c_fc / mlp c_proj) through the CTA-pair kernel (gemm_2cta.cuh)
   int opt_dual = 0;             // greedy decode step as two row halves half a layer out of phase (decode_forward_dual)
@@ -1359,6 +1360,14 @@ struct rgrg_engine {
       fp.step_ptr = sp;
       fp.attn_o = v.attn_o;
       fp.M = v.rows;
+      // spread the rows evenly over as many M tiles as fit the SMs (16 CTAs per tile): 928 rows -> 9 tiles of 104 rows on 144
+      // SMs instead of 7 full tiles + one quarter tile on 128; the LayerNorm head needs the 128-row tiling
+      {
+        const int min_tiles = ceil_div(v.rows, tc::BM);
+        const int sm_tiles = std::max(1, tc::num_sms() / 16);
+        const int tiles = (opt_attn_balance && !head) ? std::max(min_tiles, std::min(sm_tiles, ceil_div(v.rows, 32))) : min_tiles;
+        fp.rows_per_tile = (opt_attn_balance && !head) ? ceil_div(v.rows, tiles) : tc::BM;
+      }
       fp.l2_ahead = opt_l2_ahead;
       if (head) {
         fp.h = v.h;
@@ -1988,6 +1997,7 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "dual") e->opt_dual = value;
   else if (k == "gemm_2cta") e->opt_gemm_2cta = value;
   else if (k == "gemm_2cta_stages") e->opt_gemm_2cta_stages = value;
+  else if (k == "attn_balance") e->opt_attn_balance = value;
   else if (k == "l2_ahead") e->opt_l2_ahead = value;
   else if (k == "attn_occ") e->opt_attn_occ = value;
   else if (k == "cattn_bn") e->opt_cattn_bn = value;

@@ -37,8 +37,8 @@ base = run(0)
 print("full step (fused attention, CTA-pair projections): %.3f ms" % base, flush=True)
 print("  gemm_2cta=0                       : %.3f ms" % run(0, gemm_2cta=0), flush=True)
 eng.set_option("gemm_2cta", 1)
-for stg in (3, 4, 6):
-    print("  gemm_2cta_stages=%d                : %.3f ms" % (stg, run(0, gemm_2cta_stages=stg)), flush=True)
+print("  attn_balance=0 (128-row tiles)    : %.3f ms" % run(0, attn_balance=0), flush=True)
+eng.set_option("attn_balance", 1)
 if "variants" in sys.argv:
     print("  dual=1 (two halves out of phase)  : %.3f ms" % run(0, dual=1), flush=True)
     eng.set_option("dual", 0)
