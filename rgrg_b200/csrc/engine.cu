@@ -246,6 +246,7 @@ struct rgrg_engine {
   int opt_attn_occ = 7;    // CTAs per SM the stand-alone attention kernel is compiled for (5: 88 regs, 6: 78, 7: 72, 8: 64)
   int opt_ablate = 0;  // tuning only: bit mask of decode-step kernels to skip (results become meaningless, timing attributes cost)
   bool pdl_now = false;  // set while the decode step is being issued: its kernels carry the PDL launch attribute
+  bool force_2cta = false;    // GEMM test entry: the pair kernel whatever the problem size
   bool use_2cta_now = false;  // set while the decode projections are issued (and by the GEMM test entry): CTA-pair tiles
   std::unordered_map<std::string, HostRef> host;
   std::vector<void*> weight_allocs;
@@ -336,7 +337,9 @@ struct rgrg_engine {
     if (W.K % 64 != 0) throw std::runtime_error("GEMM K must be a multiple of 64");
     const int mt = ceil_div(M, tc::BM);
     if constexpr (!Epi::kDirect) {
-      if (use_2cta_now && W.N % tc2::BN == 0) {  // decode projections: CTA pairs on 256 x 256 tiles (gemm_2cta.cuh)
+      // decode projections: CTA pairs on 256 x 256 tiles (gemm_2cta.cuh) while one wave of pairs covers the problem; beyond that
+      // the persistent 1-CTA kernel (epilogue of tile i overlapped with the main loop of tile i+1) is the better shape
+      if (use_2cta_now && W.N % tc2::BN == 0 && (force_2cta || 2 * ceil_div(mt, 2) * (W.N / tc2::BN) <= tc::num_sms())) {
         tc2::Shape s2{};
         s2.M = M;
         s2.N = W.N;
@@ -378,7 +381,7 @@ struct rgrg_engine {
       return;
     }
     if ((W.K / 64) % splits) throw std::runtime_error("split-K factor must divide K / 64");
-    if (use_2cta_now && W.N % tc2::BN == 0) {
+    if (use_2cta_now && W.N % tc2::BN == 0 && (force_2cta || 2 * ceil_div(ceil_div(M, tc::BM), 2) * (W.N / tc2::BN) * splits <= tc::num_sms())) {
       tc2::Shape s2{};
       s2.M = M;
       s2.N = W.N;
@@ -2369,11 +2372,11 @@ int rgrg_gemm_bf16(rgrg_engine_t* e, const void* A_dev, const void* W_dev, const
     const bf16* A = static_cast<const bf16*>(A_dev);
     try {
       if (impl != 2) L.make_maps();
-      if (impl == 7 || impl == 8) e->use_2cta_now = true;  // CTA-pair kernel: plain (7) / split-K (8)
+      if (impl == 7 || impl == 8) e->use_2cta_now = e->force_2cta = true;  // CTA-pair kernel: plain (7) / split-K (8)
       struct Reset2 {
-        bool& f;
-        ~Reset2() { f = false; }
-      } reset2{e->use_2cta_now};
+        bool &f, &g;
+        ~Reset2() { f = g = false; }
+      } reset2{e->use_2cta_now, e->force_2cta};
       if (impl == 6 || impl == 8) {  // the decoder's split-K form: 4 K slices -> fp32 partial sums, reduced (+ bias) afterwards
         if (act != ACT_NONE) throw std::runtime_error("split-K test path has no activation");
         DevBuf parts;
