@@ -80,6 +80,8 @@ struct Params {
   const float* parts;    // split-K partial sums of the preceding projection (null: plain LayerNorm of h)
   size_t part_stride;
   const float* res_bias;
+  long long* trace;      // tuning: [2][8] timestamps of the first / last CTA (entry, setup done, predecessor done, -, -,
+                         // accumulator ready, attention done, exit)
   unsigned* counters;    // [m_tiles] arrival counters of the LayerNorm-head group barrier (common.cuh)
   int launch_idx, launches_per_step;
 };
@@ -222,6 +224,7 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
   uint64_t* att_bar = tmem_full_bar + 1;  // [ATT_WARPS][NSLOT]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(att_bar + ATT_WARPS * NSLOT);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) trace_mark(p.trace, 0);
   const int head = blockIdx.x & 15, m_blk = blockIdx.x >> 4;  // the 16 heads of an M tile are consecutive CTAs (one cluster)
 
   if (warp == 0 && lane == 0) {
@@ -245,6 +248,7 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   griddep_launch_dependents();  // dependents may be scheduled; they block at their own griddep_wait until this grid completes
+  if (threadIdx.x == 0) trace_mark(p.trace, 1);
 
   // the weight tiles never depend on the predecessor kernel: start streaming them before waiting for it
   if (warp == 0 && lane == 0) {
@@ -257,6 +261,7 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
     }
   }
   griddep_wait();
+  if (threadIdx.x == 0) trace_mark(p.trace, 2);
 
   if constexpr (LN_HEAD) {
     // rows [m_blk*128 + head*8, +8) of the M tile: h += bias + split-K partial sums of the preceding projection,
@@ -330,6 +335,7 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
     // ---- epilogue: TMEM -> (+bias, bf16) -> q / k_new / v_new tiles (+ KV-cache append)
     tc::mbar_wait(tmem_full_bar, 0);
     tc::tc_fence_after();
+    if (warp == 2 && lane == 0) trace_mark(p.trace, 5);
     {
       const int q4 = warp & 3;           // TMEM lane quarter this warp may read
       const int grp = aw >> 2;           // which of the AW / 4 warps of that quarter: takes 16-column chunks grp, grp + AW/4, ...
@@ -476,9 +482,11 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
       }
     }
   }
+  if (warp == 2 && lane == 0) trace_mark(p.trace, 6);
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+  if (threadIdx.x == 0) trace_mark(p.trace, 7);
 }
 
 template <int AW, int NSLOT, bool LN_HEAD, int ALG>

@@ -81,6 +81,17 @@ __device__ __forceinline__ void group_barrier(unsigned* ctr, unsigned target) {
   asm volatile("fence.proxy.async;" ::: "memory");
 }
 
+// tuning: nanosecond timestamps comparable across SMs (decode-step timeline, tools/decode_timeline.py)
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// slot `i` of this CTA's record when tracing is on and this is the first or the last CTA of the grid
+__device__ __forceinline__ void trace_mark(long long* trace, int i) {
+  if (trace && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) trace[(blockIdx.x == 0 ? 0 : 8) + i] = global_ns();
+}
+
 __device__ __forceinline__ float bf2f(bf16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ bf16 f2bf(float v) { return __float2bfloat16_rn(v); }
 

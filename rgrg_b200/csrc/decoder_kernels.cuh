@@ -99,8 +99,9 @@ template <int NPARTS>
 __global__ void __launch_bounds__(128) layernorm_kernel(float* __restrict__ h, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, bf16* __restrict__ out, int rows,
                                                         const float* __restrict__ parts, size_t part_stride,
-                                                        const float* __restrict__ res_bias) {
+                                                        const float* __restrict__ res_bias, long long* trace) {
   __shared__ float s_red[2][4];
+  if (threadIdx.x == 0) trace_mark(trace, 0);
   // parameters do not depend on the predecessor kernel: fetch them before waiting for it (PDL)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c0 = tid * 8;
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(128) layernorm_kernel(float* __restrict__ h, c
   }
   griddep_launch_dependents();  // dependents may be scheduled now; they block at their own griddep_wait until this grid completes
   griddep_wait();
+  if (threadIdx.x == 0) trace_mark(trace, 2);
   const int row = blockIdx.x;
   float* hp = h + static_cast<size_t>(row) * D + c0;
   float v[8];
@@ -159,6 +161,7 @@ __global__ void __launch_bounds__(128) layernorm_kernel(float* __restrict__ h, c
 #pragma unroll
   for (int e = 0; e < 8; ++e) o[e] = (v[e] - mean) * rstd * g[e] + b[e];
   *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * D + c0) = pack8(o);
+  if (threadIdx.x == 0) trace_mark(trace, 7);
 }
 
 // K18  single-query attention over the in-place KV cache (language_model.py:84-114 for a 1-token query):

@@ -67,6 +67,12 @@ struct HostRef {
 };
 
 // K-major bf16 weight [N, K] + fp32 bias, with TMA maps for both N-tile widths
+// epilogue types that can leave through gemm_2cta.cuh's TMA-store path (EpiStoreT without a residual)
+template <class E, class = void>
+struct TmaOutOk : std::false_type {};
+template <class E>
+struct TmaOutOk<E, std::void_t<decltype(E::kTmaOut)>> : std::bool_constant<E::kTmaOut> {};
+
 struct Linear {
   bf16* w = nullptr;
   float* bias = nullptr;
@@ -232,7 +238,17 @@ struct rgrg_engine {
   int opt_detector_precise = 0;  // fp32 detector (parity mode, see run_detect)
   int opt_fused_attn = 1;  // greedy decode: c_attn + KV append + attention as ONE head-aligned kernel (attn_fused.cuh)
   int opt_ln_head = 0;     // LayerNorm (+ split-K reduce + residual) as the cluster-cooperative head of the consumer GEMM
+  int opt_trace = 0;            // tuning: per-kernel timestamps of the decode step (first / last CTA), read with debug "decode_trace"
+  DevBuf trace_buf;             // [slots][2][8] int64
+  int trace_slot = 0;
+  long long* trace_ptr() {
+    if (!opt_trace) return nullptr;
+    trace_buf.ensure(256 * 16 * 8);
+    if (trace_slot >= 256) return nullptr;
+    return trace_buf.as<long long>() + static_cast<size_t>(trace_slot++) * 16;
+  }
   int opt_attn_balance = 1;     // fused attention: rows spread evenly over (#SMs / 16) M tiles instead of 128-row tiles
+  int opt_epi_tma = 1;          // CTA-pair kernel: plain epilogues leave through shared-memory slabs + TMA stores
   int opt_gemm_2cta_stages = 6; // its TMA ring depth: 6 (one CTA per SM) / 4 / 3 (two CTAs per SM: prologue overlaps the predecessor's epilogue)
   int opt_gemm_2cta = 1;        // decode projections (c_proj / c_fc / mlp c_proj) through the CTA-pair kernel (gemm_2cta.cuh)
   int opt_dual = 0;             // greedy decode step as two row halves half a layer out of phase (decode_forward_dual)
@@ -299,7 +315,7 @@ struct rgrg_engine {
                      &prop_scores, &prop_count, &roi_off, &pooled, &f6, &f7, &pred_out, &detected, &top_idx,
                      &top_scores, &top_boxes, &mean2048, &trf, &s0, &s1, &sel_logits, &selected, &sel_rows, &num_sel, &abn_logits, &abnormal,
                      &lm_in, &kv_cache, &h, &x, &q, &attn_o, &mlp_mid, &a1, &img, &part_val, &part_idx, &ids,
-                     &unfinished, &unf_count, &step, &logits_tmp, &splitk_parts, &ln_counters, &blob_dev, &gather_dev, &preproc_src, &preproc_out, &p_act[0], &p_act[1], &p_t1, &p_t2, &p_idb, &p_sub, &p_col, &p_c1, &p_feats, &p_rpn_t, &p_pooled, &p_f6, &p_f7, &b_ids2, &b_anc[0], &b_anc[1], &b_scores, &b_cand_score,
+                     &unfinished, &unf_count, &step, &logits_tmp, &splitk_parts, &ln_counters, &trace_buf, &blob_dev, &gather_dev, &preproc_src, &preproc_out, &p_act[0], &p_act[1], &p_t1, &p_t2, &p_idb, &p_sub, &p_col, &p_c1, &p_feats, &p_rpn_t, &p_pooled, &p_f6, &p_f7, &b_ids2, &b_anc[0], &b_anc[1], &b_scores, &b_cand_score,
                      &b_cand_token, &b_cand_beam, &b_hyp_score, &b_hyp_len, &b_hyp_tok, &b_hyp_count, &b_worst, &b_done, &b_not_done, &b_part_m, &b_part_l, &b_part_val, &b_part_idx};
     for (DevBuf* b : all) b->release();
   }
@@ -318,6 +334,24 @@ struct rgrg_engine {
   template <class Epi>
   void simt_f32(const float* A, const float* Wt, int M, int N, int K, const Epi& ep, cudaStream_t st) {
     simt::launch<float, float, Epi>(A, Wt, M, N, K, ep, st);
+  }
+
+  // CTA-pair kernel; plain bias / activation epilogues (c_fc, the split-K partial sums) leave through TMA stores
+  template <class Epi>
+  void launch_pair(const CUtensorMap& tmA2, const Linear& W, const tc2::Shape& s2, const Epi& epi, cudaStream_t st) {
+    if constexpr (TmaOutOk<Epi>::value) {
+      const int splits = s2.k_splits > 1 ? s2.k_splits : 1;
+      const bool layout_ok = epi.ldc == W.N && (splits == 1 || epi.split_stride == static_cast<size_t>(s2.M) * W.N);
+      if (opt_epi_tma && opt_gemm_2cta_stages >= 4 && layout_ok) {
+        const CUtensorMap tmC = tc2::make_tmap_out(epi.out, s2.M, W.N, splits, Epi::kOutBf16);
+        if (opt_gemm_2cta_stages == 4) tc2::launch<Epi, 4, true>(tmA2, W.tm[1], tmC, s2, epi, st, pdl_now);
+        else tc2::launch<Epi, 6, true>(tmA2, W.tm[1], tmC, s2, epi, st, pdl_now);
+        return;
+      }
+    }
+    if (opt_gemm_2cta_stages == 3) tc2::launch<Epi, 3>(tmA2, W.tm[1], tmA2, s2, epi, st, pdl_now);
+    else if (opt_gemm_2cta_stages == 4) tc2::launch<Epi, 4>(tmA2, W.tm[1], tmA2, s2, epi, st, pdl_now);
+    else tc2::launch<Epi, 6>(tmA2, W.tm[1], tmA2, s2, epi, st, pdl_now);
   }
 
   template <class Epi>
@@ -346,10 +380,9 @@ struct rgrg_engine {
         s2.k_iters = W.K / 64;
         s2.m_pairs = ceil_div(mt, 2);
         s2.n_tiles = W.N / tc2::BN;
+        s2.trace = trace_ptr();
         CUtensorMap tmA2 = tc::make_tmap_2d(A, M, W.K, 128);
-        if (opt_gemm_2cta_stages == 3) tc2::launch<Epi, 3>(tmA2, W.tm[1], s2, epi, st, pdl_now);
-        else if (opt_gemm_2cta_stages == 4) tc2::launch<Epi, 4>(tmA2, W.tm[1], s2, epi, st, pdl_now);
-        else tc2::launch<Epi, 6>(tmA2, W.tm[1], s2, epi, st, pdl_now);
+        launch_pair(tmA2, W, s2, epi, st);
         ++launches;
         return;
       }
@@ -389,10 +422,9 @@ struct rgrg_engine {
       s2.k_splits = splits;
       s2.m_pairs = ceil_div(ceil_div(M, tc::BM), 2);
       s2.n_tiles = W.N / tc2::BN;
+      s2.trace = trace_ptr();
       CUtensorMap tmA2 = tc::make_tmap_2d(A, M, W.K, 128);
-      if (opt_gemm_2cta_stages == 3) tc2::launch<decltype(ep), 3>(tmA2, W.tm[1], s2, ep, st, pdl_now);
-      else if (opt_gemm_2cta_stages == 4) tc2::launch<decltype(ep), 4>(tmA2, W.tm[1], s2, ep, st, pdl_now);
-      else tc2::launch<decltype(ep), 6>(tmA2, W.tm[1], s2, ep, st, pdl_now);
+      launch_pair(tmA2, W, s2, ep, st);
       ++launches;
       return;
     }
@@ -1341,9 +1373,9 @@ struct rgrg_engine {
     ProfScope ps(this, "layernorm", st);
     if (!(opt_ablate & 2)) {
       if (v.pending_bias)
-        launch_kernel(dec::layernorm_kernel<4>, dim3(v.rows), dim3(128), 0, st, pdl_now, v.h, g, b, v.x, v.rows, v.parts, v.pstride, v.pending_bias);
+        launch_kernel(dec::layernorm_kernel<4>, dim3(v.rows), dim3(128), 0, st, pdl_now, v.h, g, b, v.x, v.rows, v.parts, v.pstride, v.pending_bias, trace_ptr());
       else
-        launch_kernel(dec::layernorm_kernel<0>, dim3(v.rows), dim3(128), 0, st, pdl_now, v.h, g, b, v.x, v.rows, v.parts, v.pstride, v.pending_bias);
+        launch_kernel(dec::layernorm_kernel<0>, dim3(v.rows), dim3(128), 0, st, pdl_now, v.h, g, b, v.x, v.rows, v.parts, v.pstride, v.pending_bias, trace_ptr());
       ++launches;
     }
     v.pending_bias = nullptr;
@@ -1372,6 +1404,7 @@ struct rgrg_engine {
         fp.rows_per_tile = (opt_attn_balance && !head) ? ceil_div(v.rows, tiles) : tc::BM;
       }
       fp.l2_ahead = opt_l2_ahead;
+      fp.trace = trace_ptr();
       if (head) {
         fp.h = v.h;
         fp.x = v.x;
@@ -1522,6 +1555,7 @@ struct rgrg_engine {
   // one greedy decode step over all rows
   int decode_step(int rows, const dec::GreedyState& g, float* logits_out, cudaStream_t st) {
     const int before = static_cast<int>(launches);
+    trace_slot = 0;
     if (opt_dual && rows >= 2 * tc::BM && decode_use_fused() && !prof_on) decode_forward_dual(rows, g.ids, g.ids_ld, st);
     else decode_forward(rows, g.ids, g.ids_ld, st);
     decode_head(rows, g, logits_out, st);
@@ -2000,7 +2034,9 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "dual") e->opt_dual = value;
   else if (k == "gemm_2cta") e->opt_gemm_2cta = value;
   else if (k == "gemm_2cta_stages") e->opt_gemm_2cta_stages = value;
+  else if (k == "epi_tma") e->opt_epi_tma = value;
   else if (k == "attn_balance") e->opt_attn_balance = value;
+  else if (k == "trace") e->opt_trace = value;
   else if (k == "l2_ahead") e->opt_l2_ahead = value;
   else if (k == "attn_occ") e->opt_attn_occ = value;
   else if (k == "cattn_bn") e->opt_cattn_bn = value;
@@ -2456,13 +2492,13 @@ int rgrg_gemm_bench(rgrg_engine_t* e, int M, int N, int K, int bn, int iters, in
           s2.k_iters = K / 64;
           s2.m_pairs = ceil_div(ceil_div(M, 128), 2);
           s2.n_tiles = N / 256;
-          tc2::launch<decltype(ep), 6>(tmA, L.tm[1], s2, ep, st, false);
+          tc2::launch<decltype(ep), 6>(tmA, L.tm[1], tmA, s2, ep, st, false);
         } else {
           e->launch_bn(bn, tmA, L, s, ep, st);
         }
         if (interleave)
           dec::layernorm_kernel<0><<<M, 128, 0, st>>>(H.as<float>(), G.as<float>(), G.as<float>(), A.as<bf16>(), M, nullptr, 0,
-                                                                  nullptr);
+                                                                  nullptr, nullptr);
       }
       if (rep == 1) CUDA_CHECK(cudaEventRecord(b, st));
     }
@@ -2523,6 +2559,7 @@ int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst, size_t b
     else if (n == "proposal_scores") b = &e->prop_scores;
     else if (n == "selection_logits") b = &e->sel_logits;
     else if (n == "abnormal_logits") b = &e->abn_logits;
+    else if (n == "decode_trace") b = &e->trace_buf;
     else if (n == "region_features_2048") b = &e->mean2048;
     else if (n == "fc7") b = &e->f7;
     else if (n.rfind("max_clusters_", 0) == 0) {  // tuning: co-resident clusters of the given size for a 216 KB-smem GEMM CTA

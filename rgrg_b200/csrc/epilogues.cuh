@@ -45,6 +45,19 @@ struct EpiStoreT {
   __device__ __forceinline__ void init(State& s, int split) const { s.split_off = split * split_stride; }
   __device__ __forceinline__ void finish(State&, int, int) const {}
 
+  // the value part alone (bias + activation), for kernels that store the tile themselves (gemm_2cta.cuh's TMA-store epilogue)
+  static constexpr bool kTmaOut = (RES == RES_NONE);
+  static constexpr bool kOutBf16 = OUT_BF16;
+  template <int NV>
+  __device__ __forceinline__ void transform(int col0, float* o) const {
+    if constexpr (BIAS) add_vec_f32<NV>(o, bias + col0);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      if constexpr (ACT == ACT_RELU) o[j] = fmaxf(o[j], 0.0f);
+      if constexpr (ACT == ACT_GELU_NEW) o[j] = gelu_new(o[j]);
+    }
+  }
+
   template <int NV>
   __device__ __forceinline__ void apply(State& st, int row, int col0, const float* v, int N) const {
     const size_t base = static_cast<size_t>(row) * ldc + col0 + st.split_off;

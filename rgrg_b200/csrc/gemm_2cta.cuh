@@ -11,7 +11,12 @@
 //   warp 0  TMA producer (both CTAs; loads signal the LEADER's full barrier: cp.async.bulk.tensor...cta_group::2)
 //   warp 1  TMEM allocator (both CTAs, cta_group::2) + MMA issuer (leader CTA only); tcgen05.commit multicasts the
 //           "stage free" / "accumulator ready" arrivals to both CTAs
-//   warps 2..9 epilogue: each CTA drains its own 128 accumulator rows (same code path as gemm_tc.cuh)
+//   warps 2..9 epilogue: each CTA drains its own 128 accumulator rows.  Two variants:
+//           TMA_OUT = false: the scheme of gemm_tc.cuh (transpose through shared memory, 16-byte global stores);
+//           TMA_OUT = true (plain bias / activation epilogues): TMEM -> registers -> 128B-swizzled 32-row slabs in the (by then
+//           idle) operand ring -> `cp.async.bulk.tensor` stores.  A timeline of the decode step (tools/decode_timeline.py)
+//           showed the first variant spending 5-7 us per full tile on its global stores (1 us on a tile whose rows are
+//           all past M, i.e. without the stores; no faster with 16 warps) — as long as the 16-k-block main loop.
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -23,7 +28,10 @@ constexpr int HALF_N = BN / 2;   // W rows each CTA stages
 constexpr int A_BYTES = tc::BM * tc::BK * 2;      // 16 KB
 constexpr int B_BYTES = HALF_N * tc::BK * 2;      // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // per CTA
-constexpr int STG_BYTES = tc::EPI_WARPS * tc::STG_FLOATS * 4;
+constexpr int EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int SLAB_BYTES = 32 * 128;             // TMA-store slab: 32 rows x 128 B (32 fp32 or 64 bf16 columns)
+constexpr int STG_BYTES = EPI_WARPS * tc::STG_FLOATS * 4;
 // STAGES = 6: 209 KB, one CTA per SM.  STAGES = 3: 113 KB — two CTAs (2 x 256 TMEM columns) fit on an SM, so the
 // prologue of the next projection kernel overlaps the epilogue of the current one under PDL.
 template <int STAGES>
@@ -39,6 +47,8 @@ struct Shape {
   int k_iters;            // 64-wide K blocks in total
   int m_pairs, n_tiles;   // pair-tiles: m_pairs x n_tiles (x k_splits)
   int k_splits;           // 0/1 = off
+  long long* trace;       // tuning: [2][8] timestamps of the first / last CTA (entry, setup done, predecessor done, first MMA,
+                          // last MMA issued, accumulator ready, epilogue done, exit)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -68,6 +78,12 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t desc_a, 
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// shared memory (128B-swizzled slab of 32 rows) -> global through the output tensor map {N, M, splits}; rows past M are clipped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(tc::smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // arrives on the barrier at this shared-memory offset in BOTH CTAs once all MMAs issued so far have completed
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -76,9 +92,10 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                : "memory");
 }
 
-template <class Epi, int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NUM_THREADS, 1)
-    gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Shape s, const Epi epi) {
+template <class Epi, int STAGES, bool TMA_OUT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+    gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmC, const Shape s, const Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int BAR_OFFSET = Layout<STAGES>::BAR_OFFSET, STG_OFFSET = Layout<STAGES>::STG_OFFSET;
@@ -89,6 +106,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NUM_THREADS, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
+  if (threadIdx.x == 0) trace_mark(s.trace, 0);
 
   // pair-tile of this cluster
   int tile = blockIdx.x >> 1;
@@ -123,6 +141,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NUM_THREADS, 1)
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   griddep_launch_dependents();
+  if (threadIdx.x == 0) trace_mark(s.trace, 1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -133,6 +152,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NUM_THREADS, 1)
         tma_load_2d_2sm(smem + i * STAGE_BYTES + A_BYTES, &tmB, &full_bar[i], (kb0 + i) * tc::BK, n_blk * BN + static_cast<int>(rank) * HALF_N);
       }
       griddep_wait();
+      trace_mark(s.trace, 2);
       for (int kb = 0; kb < kpt; ++kb) {
         const int st = kb % STAGES;
         uint8_t* a_dst = smem + st * STAGE_BYTES;
@@ -152,6 +172,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NUM_THREADS, 1)
         const int st = kb % STAGES;
         tc::mbar_wait(&full_bar[st], (kb / STAGES) & 1);
         tc::tc_fence_after();
+        if (kb == 0) trace_mark(s.trace, 3);
         const uint32_t a_addr = tc::smem_u32(smem + st * STAGE_BYTES);
         const uint64_t a_desc = tc::make_sw128_kmajor_desc(a_addr);
         const uint64_t b_desc = tc::make_sw128_kmajor_desc(a_addr + A_BYTES);
@@ -160,16 +181,62 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NUM_THREADS, 1)
         umma_commit_2sm(&empty_bar[st]);  // both CTAs' ring slots reusable once these MMAs have read them
       }
       umma_commit_2sm(tmem_full_bar);  // both CTAs' accumulator halves complete
+      trace_mark(s.trace, 4);
     }
   } else {
     griddep_wait();
     // ---- epilogue: this CTA's 128 accumulator rows x 256 columns (same scheme as tc::Pipe::epilogue, one tile)
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int grp = (warp - 2) >> 2;  // which of the warps of this lane quarter
     float* stg = reinterpret_cast<float*>(smem + STG_OFFSET) + (warp - 2) * tc::STG_FLOATS;
     tc::mbar_wait(tmem_full_bar, 0);
     tc::tc_fence_after();
+    if (warp == 2 && lane == 0) trace_mark(s.trace, 5);
     const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    if constexpr (TMA_OUT) {
+      // All MMAs have completed (tmem_full), so every TMA load has landed and been consumed: the operand ring is free.
+      // This warp owns rows [q * 32, +32) x columns [grp * COLS, +COLS) of the CTA's tile, in slabs of 128 B per row.
+      constexpr int COLS = BN / (EPI_WARPS / 4);                      // 128
+      constexpr int SLAB_COLS = Epi::kOutBf16 ? 64 : 32;
+      constexpr int SLABS = COLS / SLAB_COLS;
+      static_assert(EPI_WARPS * SLABS * SLAB_BYTES <= STAGES * STAGE_BYTES, "slabs must fit in the operand ring");
+      const int m0 = m_blk * tc::BM + q * 32;
+      uint8_t* my_slabs = smem + (warp - 2) * SLABS * SLAB_BYTES;
+      const int sw = lane & 7;
+      if (m0 < s.M) {
+#pragma unroll 1
+        for (int b = 0; b < SLABS; ++b) {
+          uint8_t* slab_row = my_slabs + b * SLAB_BYTES + lane * 128;
+#pragma unroll
+          for (int h2 = 0; h2 < SLAB_COLS / 32; ++h2) {
+            const int c = grp * COLS + b * SLAB_COLS + h2 * 32;
+            uint32_t v[32];
+            tc::tmem_ld_32x32b_x16(t_addr + c, v);
+            tc::tmem_ld_32x32b_x16(t_addr + c + 16, v + 16);
+            tc::tmem_ld_wait();
+            float o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+            epi.template transform<32>(n_blk * BN + c, o);
+            if constexpr (Epi::kOutBf16) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(slab_row + (((h2 * 4 + j) ^ sw) << 4)) = pack8(o + 8 * j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(slab_row + ((j ^ sw) << 4)) = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmC, my_slabs + b * SLAB_BYTES, n_blk * BN + grp * COLS + b * SLAB_COLS, m0, split);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the reads
+      }
+    } else {
     typename Epi::State est;
     epi.init(est, split);
     int rows[2];
@@ -181,7 +248,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NUM_THREADS, 1)
     }
     const int sw_w = (lane >> 1) & 3;
 #pragma unroll 1
-    for (int c = half * 16; c < BN; c += 32) {
+    for (int c = grp * 16; c < BN; c += 16 * (EPI_WARPS / 4)) {
       uint32_t v[16];
       tc::tmem_ld_32x32b_x16(t_addr + c, v);
       tc::tmem_ld_wait();
@@ -205,15 +272,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc::NUM_THREADS, 1)
       }
       __syncwarp();
     }
+    }
   }
+  if (warp == 2 && lane == 0) trace_mark(s.trace, 6);
   tc::tc_fence_before();
   cluster_sync();  // nobody frees TMEM or exits while the peer may still signal / read
+  if (threadIdx.x == 0) trace_mark(s.trace, 7);
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
 }
 
-template <class Epi, int STAGES>
-inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Shape& s, const Epi& epi, cudaStream_t stream, bool pdl) {
-  auto kern = gemm_2cta_kernel<Epi, STAGES>;
+// output map for the TMA-store epilogue: row-major [splits][M][N] (fp32 partial sums) or [M][N] (splits = 1); slabs of 32 rows x 128 B
+inline CUtensorMap make_tmap_out(const void* ptr, uint64_t M, uint64_t N, uint64_t splits, bool bf16_out) {
+  CUtensorMap m;
+  const uint64_t es = bf16_out ? 2 : 4;
+  cuuint64_t dims[3] = {N, M, splits};
+  cuuint64_t strides[2] = {N * es, M * N * es};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(128 / es), 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = tc::encode_fn()(&m, bf16_out ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr),
+                               dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(out) failed: " + std::to_string((int)r));
+  return m;
+}
+
+// tmC: only read when TMA_OUT (pass tmA otherwise)
+template <class Epi, int STAGES, bool TMA_OUT = false>
+inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const Shape& s, const Epi& epi,
+                   cudaStream_t stream, bool pdl) {
+  auto kern = gemm_2cta_kernel<Epi, STAGES, TMA_OUT>;
   constexpr int SMEM_TOTAL = Layout<STAGES>::TOTAL;
   static bool configured = false;  // one engine device per process (rgrg_create enforces it)
   if (!configured) {
@@ -223,7 +310,7 @@ inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Shape& 
   const int pairs = s.m_pairs * s.n_tiles * (s.k_splits > 1 ? s.k_splits : 1);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
-  cfg.blockDim = dim3(tc::NUM_THREADS);
+  cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM_TOTAL;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -231,7 +318,7 @@ inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const Shape& 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, s, epi));
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, s, epi));
 }
 
 }  // namespace tc2

@@ -77,6 +77,17 @@ def test_gemm_cta_pair_kernel(eng_bare, M, N, K):
     out = eng_bare.gemm(A, W, bias, act=2, impl=7)
     g = 0.5 * ref * (1 + torch.tanh(0.7978845608028654 * (ref + 0.044715 * ref ** 3)))
     assert (out - g).abs().max().item() <= 2e-3 * max(1.0, g.abs().max().item())
+    # the TMA-store epilogue (default) and the register epilogue write the same bits
+    try:
+        eng_bare.set_option("epi_tma", 0)
+        out0 = eng_bare.gemm(A, W, bias, act=2, impl=7)
+        assert torch.equal(out, out0)
+        if (K // 64) % 4 == 0:
+            a1 = eng_bare.gemm(A, W, bias, act=0, impl=8)
+            eng_bare.set_option("epi_tma", 1)
+            assert torch.equal(a1, eng_bare.gemm(A, W, bias, act=0, impl=8))
+    finally:
+        eng_bare.set_option("epi_tma", 1)
 
 
 @pytest.mark.parametrize("act", [1, 2])

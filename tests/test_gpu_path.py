@@ -330,10 +330,12 @@ def test_cta_pair_projections_are_bit_identical(model, oracle_detail):
             b = eng.lm_generate(feats[:rows], 16)
             _opts(eng, cuda_graph=0)
             c = eng.lm_generate(feats[:rows], 16)
-            _opts(eng, cuda_graph=1)
-            assert np.array_equal(a, b) and np.array_equal(a, c), rows
+            _opts(eng, cuda_graph=1, epi_tma=0)  # register epilogue instead of the shared-memory slabs + TMA stores
+            d = eng.lm_generate(feats[:rows], 16)
+            _opts(eng, epi_tma=1)
+            assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, d), rows
     finally:
-        _opts(eng, gemm_2cta=1, cuda_graph=1)
+        _opts(eng, gemm_2cta=1, cuda_graph=1, epi_tma=1)
 
 
 def test_two_halves_schedule_is_bit_identical_to_single_chain(model, oracle_detail):
