@@ -330,6 +330,11 @@ def main():
 
     from rgrg_b200 import parallel
 
+    for kv in filter(None, os.environ.get("RGRG_OPTS", "").split(",")):  # tuning only: engine options, e.g. RGRG_OPTS=epi_tma=0
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
+        log("engine option %s=%s" % (k, v))
+
     native_gather = False
     if world > 1 and args.gather == "native":
         try:

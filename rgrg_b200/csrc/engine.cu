@@ -248,6 +248,7 @@ struct rgrg_engine {
     return trace_buf.as<long long>() + static_cast<size_t>(trace_slot++) * 16;
   }
   int opt_attn_balance = 1;     // fused attention: rows spread evenly over (#SMs / 16) M tiles instead of 128-row tiles
+  int opt_gemm_2cta_waves = 2;  // the pair kernel is used while its grid fits in this many waves (else the persistent 1-CTA kernel)
   int opt_epi_tma = 1;          // CTA-pair kernel: plain epilogues leave through shared-memory slabs + TMA stores
   int opt_gemm_2cta_stages = 6; // its TMA ring depth: 6 (one CTA per SM) / 4 / 3 (two CTAs per SM: prologue overlaps the predecessor's epilogue)
   int opt_gemm_2cta = 1;        // decode projections (c_proj / c_fc / mlp c_proj) through the CTA-pair kernel (gemm_2cta.cuh)
@@ -373,7 +374,7 @@ struct rgrg_engine {
     if constexpr (!Epi::kDirect) {
       // decode projections: CTA pairs on 256 x 256 tiles (gemm_2cta.cuh) while one wave of pairs covers the problem; beyond that
       // the persistent 1-CTA kernel (epilogue of tile i overlapped with the main loop of tile i+1) is the better shape
-      if (use_2cta_now && W.N % tc2::BN == 0 && (force_2cta || 2 * ceil_div(mt, 2) * (W.N / tc2::BN) <= tc::num_sms())) {
+      if (use_2cta_now && W.N % tc2::BN == 0 && (force_2cta || 2 * ceil_div(mt, 2) * (W.N / tc2::BN) <= opt_gemm_2cta_waves * tc::num_sms())) {
         tc2::Shape s2{};
         s2.M = M;
         s2.N = W.N;
@@ -414,7 +415,7 @@ struct rgrg_engine {
       return;
     }
     if ((W.K / 64) % splits) throw std::runtime_error("split-K factor must divide K / 64");
-    if (use_2cta_now && W.N % tc2::BN == 0 && (force_2cta || 2 * ceil_div(ceil_div(M, tc::BM), 2) * (W.N / tc2::BN) * splits <= tc::num_sms())) {
+    if (use_2cta_now && W.N % tc2::BN == 0 && (force_2cta || 2 * ceil_div(ceil_div(M, tc::BM), 2) * (W.N / tc2::BN) * splits <= opt_gemm_2cta_waves * tc::num_sms())) {
       tc2::Shape s2{};
       s2.M = M;
       s2.N = W.N;
@@ -2035,6 +2036,7 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "gemm_2cta") e->opt_gemm_2cta = value;
   else if (k == "gemm_2cta_stages") e->opt_gemm_2cta_stages = value;
   else if (k == "epi_tma") e->opt_epi_tma = value;
+  else if (k == "gemm_2cta_waves") e->opt_gemm_2cta_waves = value;
   else if (k == "attn_balance") e->opt_attn_balance = value;
   else if (k == "trace") e->opt_trace = value;
   else if (k == "l2_ahead") e->opt_l2_ahead = value;

@@ -19,6 +19,8 @@ tr = eng.debug_read("decode_trace", (256, 2, 8), np.int64).astype(np.float64)
 # slot order per layer: view_attn takes the fused kernel's slot before it launches LayerNorm 1
 names = ["ATTN", "LN1", "CPROJ", "LN2", "CFC", "MPROJ"]
 ev = ["entry", "setup", "pred-done", "mma0", "mma-issued", "acc-ready", "body-done", "exit"]
+# the fused attention kernel uses slots 3 / 4 for "tiles written" (epilogue done) and "first K/V chunk landed"
+
 for l in (11, 12):
     t0 = tr[6 * l, 0, 0]
     print("layer %d (us since the fused attention kernel's first CTA entered; first CTA | last CTA)" % l)
