@@ -8,9 +8,12 @@
 //   1. tcgen05 main loop (K = 1024: 16 k-blocks, accumulator 128 x 192 fp32 in TMEM), fed by TMA through a 3-stage ring;
 //   2. epilogue: + bias -> bf16; q / k_new / v_new -> swizzled shared-memory tiles; k_new, v_new appended in place into
 //      the KV cache at slot t+1 (the reference regrows the cache with torch.cat, language_model.py:169-170);
-//   3. attention: 8 warps, one (row, head) item per warp at a time; the cached keys / values of an item (slots 0..t,
-//      contiguous L x 128 B blocks) are streamed in 16-key chunks by cp.async.bulk into a per-warp ring of NSLOT
-//      shared-memory slots (mbarrier complete_tx), the new key / value comes from the tiles of step 2.  Optional:
+//   3. attention: AW warps, one (row, head) item per warp at a time; the cached keys / values of an item (slots 0..t: ONE
+//      contiguous block of L x 256 B, key row and value row of a slot adjacent) are streamed in 16-key chunks, one
+//      cp.async.bulk per chunk, into a per-warp ring of NSLOT shared-memory slots (mbarrier complete_tx); the new key /
+//      value comes from the tiles of step 2.  One copy per chunk matters: the timeline (tools/decode_timeline.py) showed
+//      the phase taking 44 ns per bulk copy whatever its size (1 - 2 KB) at every cache length — bound by the SM's copy
+//      issue rate, not by HBM — when keys and values were separate blocks and needed two copies per chunk.  Optional:
 //      cp.async.bulk.prefetch.L2 of the next items' blocks, issued before the main loop finishes, so HBM streams while
 //      the tensor pipe runs.
 // Arithmetic and reduction order are those of dec::attention_dev (decoder_kernels.cuh): 16-key chunks, 4 key subgroups x
@@ -42,18 +45,15 @@ constexpr int TMEM_COLS = 256;
 // AW = attention / epilogue warps per CTA (a multiple of 4: AW / 4 warps share a TMEM lane quarter); block = 64 + 32 AW threads.
 // The per-chunk work of a warp is a chain of dependent shared-memory loads, shuffles and exponentials, so the attention
 // phase scales with the number of resident warps until HBM saturates (measured: 8 warps -> 45 us per layer at 928 rows).
-// ALG 1: 16-key chunks of K and V staged together (SLOT_BYTES), arithmetic order of dec::attention_dev (bit-identical to
-//        the two-kernel path).
-// ALG 2: 32-key chunks, K only staged (32 x 128 B = SLOT_BYTES as well); lane = key for q.K, lane = dim pair for P.V with
-//        V rows read straight from global memory (coalesced 128-byte rows, prefetched into registers); ~3x fewer
-//        instructions per key (ncu on ALG 1: issue slots 64 % busy, DRAM 47 %: instruction-bound).
+// ALG 1 (the only one left): 16-key chunks, arithmetic order of dec::attention_dev (bit-identical to the two-kernel path).
+//        A lane-per-key variant (ALG 2: K staged, V rows read straight from global memory) was measured slower
+//        (profiles/r02_decode.md) and removed when the cache layout became slot-interleaved.
 template <int AW, int NSLOT, int ALG = 1>
 struct Smem {
   static constexpr int ATT_WARPS = AW;
   static constexpr int GEMM_BYTES = STAGES * STAGE_BYTES;
   static constexpr int STG_OFFSET = 3 * TILE_BYTES;  // attention phase: tiles at [0, 48 KB), staging rings after them
-  static constexpr int Q_OFFSET = STG_OFFSET + ATT_WARPS * NSLOT * SLOT_BYTES;  // ALG 2: fp32 q of the current item, 256 B per warp
-  static constexpr int ATT_BYTES = Q_OFFSET + (ALG == 2 ? ATT_WARPS * 256 : 0);
+  static constexpr int ATT_BYTES = STG_OFFSET + ATT_WARPS * NSLOT * SLOT_BYTES;
   static constexpr int BAR_OFFSET = GEMM_BYTES > ATT_BYTES ? GEMM_BYTES : ATT_BYTES;
   static constexpr int NBARS = 2 * STAGES + 1 + ATT_WARPS * NSLOT;
   static constexpr int TOTAL = BAR_OFFSET + NBARS * 8 + 16 + 1024;  // + alignment slack
@@ -70,6 +70,7 @@ struct Params {
   int M;
   int rows_per_tile;     // rows OWNED by one M tile (<= 128; the MMA still covers 128 rows, the surplus belongs to the next tile):
                          // rows are spread evenly over as many tiles as there are SMs / 16, so every CTA streams the same amount
+  int early_kv;          // 1: the first K / V chunks are requested before the epilogue instead of after it
   int l2_ahead;          // items whose K / V blocks are prefetched into L2 ahead of the consumer (0 = off; measured: no gain —
                          // neither this nor prefetching the NEXT layer's cache during the GEMM kernels, profiles/r02_decode.md)
   // optional LayerNorm head (null h = off; needs a 16-CTA cluster launch)
@@ -80,8 +81,8 @@ struct Params {
   const float* parts;    // split-K partial sums of the preceding projection (null: plain LayerNorm of h)
   size_t part_stride;
   const float* res_bias;
-  long long* trace;      // tuning: [2][8] timestamps of the first / last CTA (entry, setup done, predecessor done, -, -,
-                         // accumulator ready, attention done, exit)
+  long long* trace;      // tuning: [2][8] timestamps of the first / last CTA (entry, setup done, predecessor done, tiles written,
+                         // first K / V chunk landed, accumulator ready, attention done, exit)
   unsigned* counters;    // [m_tiles] arrival counters of the LayerNorm-head group barrier (common.cuh)
   int launch_idx, launches_per_step;
 };
@@ -98,118 +99,6 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-// ---------------------------------------------------------------------------------------------------------------
-// ALG 2 attention of one warp over its items (rows aw, aw + AW, ... of the M tile, head `head`).
-//   q.K^T : lane = key (32 keys per chunk).  The key's 128-byte row is read from the staged chunk in eight 16-byte pieces,
-//           piece index XOR-ed with (lane & 7) so that the eight lanes of a quarter-warp hit distinct banks; q (fp32, in
-//           shared memory) is read with the same permutation.
-//   softmax: online over 32-key chunks; max / sum by warp shuffles; running (max, denominator) are warp-uniform.
-//   P.V   : lane = dims (2 lane, 2 lane + 1).  V[key] rows are read from global memory as one coalesced 128-byte request
-//           per key (4 bytes per lane), all 32 of a chunk issued before the q.K^T math; p[key] is broadcast by shuffle.
-// ---------------------------------------------------------------------------------------------------------------
-template <int AW, int NSLOT>
-__device__ __forceinline__ void attention_v2(uint8_t* smem, uint64_t* att_bar, const Params& p, int aw, int lane, int head, int row0,
-                                             int n_items, int t) {
-  using L = Smem<AW, NSLOT, 2>;
-  constexpr int CK = 32;  // keys per chunk
-  const int Lc = t + 1, Ltot = Lc + 1;
-  const int nsc = (Lc + CK - 1) / CK;       // staged chunks per item
-  const int nchunks = (Ltot + CK - 1) / CK;  // compute chunks per item
-  uint8_t* stg = smem + L::STG_OFFSET + aw * NSLOT * SLOT_BYTES;
-  float* qs = reinterpret_cast<float*>(smem + L::Q_OFFSET + aw * 256);
-  uint64_t* bars = att_bar + aw * NSLOT;
-  const int total = n_items * nsc;
-  auto item_row = [&](int j) { return row0 + aw + AW * j; };
-  auto issue = [&](int seq) {
-    if (lane == 0) {
-      const int j = seq / nsc, c = seq - j * nsc;
-      const uint32_t bytes = static_cast<uint32_t>(min(CK, Lc - c * CK)) * 128;
-      const int s = seq % NSLOT;
-      tc::mbar_expect_tx(&bars[s], bytes);
-      bulk_g2s(stg + s * SLOT_BYTES, p.kv.cache + p.kv.offset(p.layer, 0, item_row(j), head, c * CK), bytes, &bars[s]);
-    }
-  };
-  for (int s = 0; s < NSLOT && s < total; ++s) issue(s);
-  int seq = 0;
-  const int x7 = lane & 7;
-  for (int j = 0; j < n_items; ++j) {
-    const int rl = aw + AW * j;
-    const int row = item_row(j);
-    const int rx = rl & 7;
-    // q (bf16 tile, swizzled) -> fp32 in this warp's 256-byte q buffer
-    __syncwarp();
-    if (lane < 8) {
-      float qf[8];
-      unpack8(*reinterpret_cast<const uint4*>(smem + rl * 128 + ((lane ^ rx) << 4)), qf);
-      *reinterpret_cast<float4*>(qs + lane * 8) = make_float4(qf[0], qf[1], qf[2], qf[3]);
-      *reinterpret_cast<float4*>(qs + lane * 8 + 4) = make_float4(qf[4], qf[5], qf[6], qf[7]);
-    }
-    const uint32_t vnew = *reinterpret_cast<const uint32_t*>(smem + 2 * TILE_BYTES + rl * 128 + (((lane >> 2) ^ rx) << 4) + (lane & 3) * 4);
-    const uint8_t* knew_row = smem + TILE_BYTES + rl * 128;
-    const bf16* Vg = p.kv.cache + p.kv.offset(p.layer, 1, row, head, 0) + 2 * lane;
-    __syncwarp();
-    float m = -INFINITY, den = 0.0f, acc0 = 0.0f, acc1 = 0.0f;
-    for (int c = 0; c < nchunks; ++c) {
-      const int c0 = c * CK;
-      // V rows of the chunk: issued first, consumed last
-      uint32_t v[CK];
-#pragma unroll
-      for (int kk = 0; kk < CK; ++kk) {
-        const int key = c0 + kk;
-        v[kk] = 0u;
-        if (key < Lc) v[kk] = __ldcg(reinterpret_cast<const uint32_t*>(Vg + static_cast<size_t>(key) * 64));
-        else if (key == Lc) v[kk] = vnew;
-      }
-      const bool staged = c < nsc;
-      const int s = seq % NSLOT;
-      if (staged) tc::mbar_wait(&bars[s], (seq / NSLOT) & 1);
-      const int key = c0 + lane;
-      const bool cached = key < Lc;
-      const uint8_t* kp = cached ? stg + s * SLOT_BYTES + lane * 128 : knew_row;
-      const int xr = cached ? 0 : rx;
-      float dot = 0.0f;
-#pragma unroll
-      for (int j8 = 0; j8 < 8; ++j8) {
-        const int cl = j8 ^ x7;  // logical 16-byte piece of the key row (dims 8 cl .. 8 cl + 7)
-        float kf[8];
-        unpack8(*reinterpret_cast<const uint4*>(kp + ((cl ^ xr) << 4)), kf);
-        const float4 qa = *reinterpret_cast<const float4*>(qs + cl * 8), qb = *reinterpret_cast<const float4*>(qs + cl * 8 + 4);
-        dot = fmaf(qa.x, kf[0], dot); dot = fmaf(qa.y, kf[1], dot); dot = fmaf(qa.z, kf[2], dot); dot = fmaf(qa.w, kf[3], dot);
-        dot = fmaf(qb.x, kf[4], dot); dot = fmaf(qb.y, kf[5], dot); dot = fmaf(qb.z, kf[6], dot); dot = fmaf(qb.w, kf[7], dot);
-      }
-      if (staged) {
-        __syncwarp();  // every lane is done reading this slot before it is refilled
-        if (seq + NSLOT < total) issue(seq + NSLOT);
-        ++seq;
-      }
-      const float sc = key < Ltot ? dot * 0.125f : -INFINITY;  // / sqrt(64)   (language_model.py:88)
-      const float m_new = fmaxf(m, warp_max(sc));               // finite: every chunk holds at least one valid key
-      const float pr = __expf(sc - m_new);                      // exp(-inf) = 0 for masked keys
-      const float corr = __expf(m - m_new);
-      den = den * corr + warp_sum(pr);
-      acc0 *= corr;
-      acc1 *= corr;
-      m = m_new;
-      const int nk = min(CK, Ltot - c0);
-#pragma unroll
-      for (int k8 = 0; k8 < CK; k8 += 8) {
-        if (k8 < nk) {
-#pragma unroll
-          for (int kk = k8; kk < k8 + 8; ++kk) {
-            const float pk = __shfl_sync(0xffffffffu, pr, kk);
-            acc0 = fmaf(pk, __uint_as_float(v[kk] << 16), acc0);
-            acc1 = fmaf(pk, __uint_as_float(v[kk] & 0xffff0000u), acc1);
-          }
-        }
-      }
-    }
-    const float inv = 1.0f / den;
-    const __nv_bfloat162 o2 = __floats2bfloat162_rn(acc0 * inv, acc1 * inv);
-    *reinterpret_cast<__nv_bfloat162*>(p.attn_o + static_cast<size_t>(row) * dec::D + head * dec::HD + 2 * lane) = o2;
-  }
-}
-
 
 template <int AW, int NSLOT, bool LN_HEAD, int ALG>
 __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -323,19 +212,37 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
     const int n_items = rows_left > aw ? (rows_left - aw + AW - 1) / AW : 0;
     const int nsc = (Lc + CHUNK_KEYS - 1) / CHUNK_KEYS;       // staged chunks per item (cached keys)
     const int nchunks = (Ltot + CHUNK_KEYS - 1) / CHUNK_KEYS;  // compute chunks per item (cached + new key)
-    const uint32_t blk_bytes = static_cast<uint32_t>(Lc) * 128;
+    const uint32_t blk_bytes = static_cast<uint32_t>(Lc) * 256;  // the item's cached keys and values, one contiguous block
     auto item_row = [&](int j) { return row0 + aw + AW * j; };
     if (p.l2_ahead > 0 && lane == 0) {
       for (int j = 0; j < p.l2_ahead && j < n_items; ++j) {
         bulk_prefetch_l2(p.kv.cache + p.kv.offset(p.layer, 0, item_row(j), head, 0), blk_bytes);
-        bulk_prefetch_l2(p.kv.cache + p.kv.offset(p.layer, 1, item_row(j), head, 0), blk_bytes);
       }
     }
+
+    // staging ring of this warp: NSLOT slots of 16 slots x (key row + value row)
+    uint8_t* stg = smem + L::STG_OFFSET + aw * NSLOT * SLOT_BYTES;
+    uint64_t* bars = att_bar + aw * NSLOT;
+    const int total = n_items * nsc;
+    auto issue = [&](int seq) {
+      if (lane == 0) {
+        const int j = seq / nsc, c = seq - j * nsc;
+        const int keys = min(CHUNK_KEYS, Lc - c * CHUNK_KEYS);
+        const uint32_t bytes = static_cast<uint32_t>(keys) * 256;  // key and value rows of a slot are adjacent: ONE copy per chunk
+        const int s = seq % NSLOT;
+        tc::mbar_expect_tx(&bars[s], bytes);
+        bulk_g2s(stg + s * SLOT_BYTES, p.kv.cache + p.kv.offset(p.layer, 0, item_row(j), head, c * CHUNK_KEYS), bytes, &bars[s]);
+      }
+    };
 
     // ---- epilogue: TMEM -> (+bias, bf16) -> q / k_new / v_new tiles (+ KV-cache append)
     tc::mbar_wait(tmem_full_bar, 0);
     tc::tc_fence_after();
     if (warp == 2 && lane == 0) trace_mark(p.trace, 5);
+    // Every MMA has completed, so the operand ring is idle; the tiles at [0, 48 KB) and the staging rings behind them do not
+    // overlap: with early_kv the first cached chunks (written by earlier steps) start streaming under the epilogue.
+    if (p.early_kv)
+      for (int s = 0; s < NSLOT && s < total; ++s) issue(s);
     {
       const int q4 = warp & 3;           // TMEM lane quarter this warp may read
       const int grp = aw >> 2;           // which of the AW / 4 warps of that quarter: takes 16-column chunks grp, grp + AW/4, ...
@@ -367,35 +274,20 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
       }
       tc::tc_fence_before();
     }
+    if (warp == 2 && lane == 0) trace_mark(p.trace, 3);
     asm volatile("bar.sync 1, %0;" ::"r"(32 * AW) : "memory");  // all attention warps: tiles complete, the GEMM ring is free for staging
 
-    if constexpr (ALG == 2) {
-      attention_v2<AW, NSLOT>(smem, att_bar, p, aw, lane, head, row0, n_items, t);
-    } else {
+    static_assert(ALG == 1, "the lane-per-key variant (ALG 2) was removed with the interleaved cache layout");
+    {
       // ---- attention
       const int sub = lane >> 3, dseg = lane & 7;
-      uint8_t* stg = smem + L::STG_OFFSET + aw * NSLOT * SLOT_BYTES;
-      uint64_t* bars = att_bar + aw * NSLOT;
-      const int total = n_items * nsc;
-      auto issue = [&](int seq) {
-        if (lane == 0) {
-          const int j = seq / nsc, c = seq - j * nsc;
-          const int keys = min(CHUNK_KEYS, Lc - c * CHUNK_KEYS);
-          const uint32_t bytes = static_cast<uint32_t>(keys) * 128;
-          const int s = seq % NSLOT;
-          tc::mbar_expect_tx(&bars[s], 2 * bytes);
-          bulk_g2s(stg + s * SLOT_BYTES, p.kv.cache + p.kv.offset(p.layer, 0, item_row(j), head, c * CHUNK_KEYS), bytes, &bars[s]);
-          bulk_g2s(stg + s * SLOT_BYTES + CHUNK_KEYS * 128, p.kv.cache + p.kv.offset(p.layer, 1, item_row(j), head, c * CHUNK_KEYS),
-                   bytes, &bars[s]);
-        }
-      };
-      for (int s = 0; s < NSLOT && s < total; ++s) issue(s);
+      if (!p.early_kv)
+        for (int s = 0; s < NSLOT && s < total; ++s) issue(s);
       int seq = 0;
       for (int j = 0; j < n_items; ++j) {
         const int rl = aw + AW * j;
         if (p.l2_ahead > 0 && lane == 0 && j + p.l2_ahead < n_items) {
           bulk_prefetch_l2(p.kv.cache + p.kv.offset(p.layer, 0, item_row(j + p.l2_ahead), head, 0), blk_bytes);
-          bulk_prefetch_l2(p.kv.cache + p.kv.offset(p.layer, 1, item_row(j + p.l2_ahead), head, 0), blk_bytes);
         }
         const int sw = (dseg ^ (rl & 7)) << 4;
         float qv[8];
@@ -411,8 +303,9 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
           const bool staged = c < nsc;
           const int s = seq % NSLOT;
           if (staged) tc::mbar_wait(&bars[s], (seq / NSLOT) & 1);
-          const uint8_t* Kb = stg + s * SLOT_BYTES;
-          const uint8_t* Vb = Kb + CHUNK_KEYS * 128;
+          if (seq == 0 && warp == 2 && lane == 0) trace_mark(p.trace, 4);
+          const uint8_t* Kb = stg + s * SLOT_BYTES;  // [key][k | v][64] as in the cache
+          const uint8_t* Vb = Kb + 128;
           float sc[4];
           uint4 vr[4];
   #pragma unroll
@@ -420,8 +313,8 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
             const int key = c0 + i * 4 + sub;
             uint4 kraw;
             if (key < Lc) {
-              kraw = *reinterpret_cast<const uint4*>(Kb + (key - c0) * 128 + dseg * 16);
-              vr[i] = *reinterpret_cast<const uint4*>(Vb + (key - c0) * 128 + dseg * 16);
+              kraw = *reinterpret_cast<const uint4*>(Kb + (key - c0) * 256 + dseg * 16);
+              vr[i] = *reinterpret_cast<const uint4*>(Vb + (key - c0) * 256 + dseg * 16);
             } else {  // key == Lc: the word of this step; beyond: masked below
               kraw = knew;
               vr[i] = vnew;

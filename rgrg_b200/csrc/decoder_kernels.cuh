@@ -202,8 +202,8 @@ __device__ __forceinline__ void attention_dev(const bf16* __restrict__ q, const 
         kp = kv.cache + kv.offset(layer, 0, prow, head, 0);
         vp = kv.cache + kv.offset(layer, 1, prow, head, 0);
       }
-      kr[i] = __ldcg(reinterpret_cast<const uint4*>(kp + static_cast<size_t>(key) * HD + dseg * 8));  // streamed once: skip L1
-      vr[i] = __ldcg(reinterpret_cast<const uint4*>(vp + static_cast<size_t>(key) * HD + dseg * 8));
+      kr[i] = __ldcg(reinterpret_cast<const uint4*>(kp + static_cast<size_t>(key) * KvGeom::SLOT_STRIDE + dseg * 8));  // streamed once: skip L1
+      vr[i] = __ldcg(reinterpret_cast<const uint4*>(vp + static_cast<size_t>(key) * KvGeom::SLOT_STRIDE + dseg * 8));
     }
   };
   uint4 kcur[4], vcur[4], knext[DOUBLE_BUFFER ? 4 : 1], vnext[DOUBLE_BUFFER ? 4 : 1];

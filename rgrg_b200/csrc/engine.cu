@@ -249,13 +249,13 @@ struct rgrg_engine {
   }
   int opt_attn_balance = 1;     // fused attention: rows spread evenly over (#SMs / 16) M tiles instead of 128-row tiles
   int opt_gemm_2cta_waves = 2;  // the pair kernel is used while its grid fits in this many waves (else the persistent 1-CTA kernel)
+  int opt_attn_early = 0;       // fused attention: request the first K / V chunks before the epilogue
   int opt_epi_tma = 1;          // CTA-pair kernel: plain epilogues leave through shared-memory slabs + TMA stores
   int opt_gemm_2cta_stages = 6; // its TMA ring depth: 6 (one CTA per SM) / 4 / 3 (two CTAs per SM: prologue overlaps the predecessor's epilogue)
   int opt_gemm_2cta = 1;        // decode projections (c_proj / c_fc / mlp c_proj) through the CTA-pair kernel (gemm_2cta.cuh)
   int opt_dual = 0;             // greedy decode step as two row halves half a layer out of phase (decode_forward_dual)
   int opt_roi_align_sep = 1;    // RoIAlign in separable form (vertical interpolation once per feature column of a bin row)
   int opt_beam_fused_head = 1;  // beam search: log-softmax + per-part top-k fused into the lm_head epilogue (0: fp32 logits in HBM)
-  int opt_attn_alg = 1;     // fused attention inner loop: 1 = order of dec::attention_dev (bit-identical to the two-kernel path), 2 = lane-per-key
   int opt_attn_warps = 16;  // fused attention: attention / epilogue warps per CTA
   int opt_attn_slots = 2;  // fused attention: shared-memory K/V ring slots per warp
   int opt_l2_ahead = 0;    // fused attention: items whose K/V blocks are prefetched into L2 ahead of the consumer
@@ -1306,16 +1306,11 @@ struct rgrg_engine {
   // (attention warps, ring slots per warp): 48 KB of q/k/v tiles + AW * NSLOT * 4 KB of K/V staging must fit in 227 KB
   template <bool LN_HEAD>
   void launch_attn_fused(const CUtensorMap& tmA, const CUtensorMap& tmW, const fa::Params& fp, cudaStream_t st) {
-    switch (opt_attn_alg * 1000 + opt_attn_warps * 10 + opt_attn_slots) {
-      case 1084: fa::launch<8, 4, LN_HEAD, 1>(tmA, tmW, fp, st, pdl_now); break;
-      case 1162: fa::launch<16, 2, LN_HEAD, 1>(tmA, tmW, fp, st, pdl_now); break;
-      case 1241: fa::launch<24, 1, LN_HEAD, 1>(tmA, tmW, fp, st, pdl_now); break;
-      case 2082: fa::launch<8, 2, LN_HEAD, 2>(tmA, tmW, fp, st, pdl_now); break;
-      case 2084: fa::launch<8, 4, LN_HEAD, 2>(tmA, tmW, fp, st, pdl_now); break;
-      case 2122: fa::launch<12, 2, LN_HEAD, 2>(tmA, tmW, fp, st, pdl_now); break;
-      case 2123: fa::launch<12, 3, LN_HEAD, 2>(tmA, tmW, fp, st, pdl_now); break;
-      case 2162: fa::launch<16, 2, LN_HEAD, 2>(tmA, tmW, fp, st, pdl_now); break;
-      default: throw std::runtime_error("unsupported (attn_alg, attn_warps, attn_slots)");
+    switch (opt_attn_warps * 10 + opt_attn_slots) {
+      case 84: fa::launch<8, 4, LN_HEAD, 1>(tmA, tmW, fp, st, pdl_now); break;
+      case 162: fa::launch<16, 2, LN_HEAD, 1>(tmA, tmW, fp, st, pdl_now); break;
+      case 241: fa::launch<24, 1, LN_HEAD, 1>(tmA, tmW, fp, st, pdl_now); break;
+      default: throw std::runtime_error("unsupported (attn_warps, attn_slots)");
     }
   }
 
@@ -1352,7 +1347,7 @@ struct rgrg_engine {
     v.parts = splitk_parts.as<float>() + static_cast<size_t>(row0) * DM * 4;  // each view keeps its 4 slices contiguous
     v.pstride = static_cast<size_t>(rows) * DM;
     v.kv = kv_geom();
-    v.kv.cache += static_cast<size_t>(row0) * 16 * ws_slots * 64;  // KvGeom::offset is linear in the row index
+    v.kv.cache += v.kv.offset(0, 0, row0, 0, 0);  // KvGeom::offset is linear in the row index
     v.ids = ids_all + static_cast<size_t>(row0) * ids_ld;
     v.ids_ld = ids_ld;
     v.counters = ln_counters.as<unsigned>() + (row0 ? 256 : 0);
@@ -1406,6 +1401,7 @@ struct rgrg_engine {
       }
       fp.l2_ahead = opt_l2_ahead;
       fp.trace = trace_ptr();
+      fp.early_kv = opt_attn_early;
       if (head) {
         fp.h = v.h;
         fp.x = v.x;
@@ -2029,13 +2025,13 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "ln_head") e->opt_ln_head = value;
   else if (k == "attn_slots") e->opt_attn_slots = value;
   else if (k == "attn_warps") e->opt_attn_warps = value;
-  else if (k == "attn_alg") e->opt_attn_alg = value;
   else if (k == "beam_fused_head") e->opt_beam_fused_head = value;
   else if (k == "roi_align_sep") e->opt_roi_align_sep = value;
   else if (k == "dual") e->opt_dual = value;
   else if (k == "gemm_2cta") e->opt_gemm_2cta = value;
   else if (k == "gemm_2cta_stages") e->opt_gemm_2cta_stages = value;
   else if (k == "epi_tma") e->opt_epi_tma = value;
+  else if (k == "attn_early") e->opt_attn_early = value;
   else if (k == "gemm_2cta_waves") e->opt_gemm_2cta_waves = value;
   else if (k == "attn_balance") e->opt_attn_balance = value;
   else if (k == "trace") e->opt_trace = value;

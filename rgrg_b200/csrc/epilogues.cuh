@@ -122,13 +122,16 @@ struct EpiStoreT {
   }
 };
 
-// KV-cache geometry: cache[layer][kv][row][head][slot][64] bf16 (slot 0 = image key/value, slot 1+t = word t).
+// KV-cache geometry: cache[layer][row][head][slot][kv][64] bf16 (slot 0 = image key/value, slot 1+t = word t).  The key row
+// and the value row of a slot are adjacent (256 B), so the cached history of one (row, head) is ONE contiguous block that
+// the fused attention kernel streams with one bulk copy per 16-slot chunk.
 struct KvGeom {
   bf16* cache;
   int rows_cap;   // row capacity of the allocation
   int slots_cap;  // slot capacity (max_length + 1)
-  __device__ __forceinline__ size_t offset(int layer, int kv, int row, int head, int slot) const {
-    return ((((static_cast<size_t>(layer) * 2 + kv) * rows_cap + row) * 16 + head) * slots_cap + slot) * 64;
+  static constexpr int SLOT_STRIDE = 128;  // elements between consecutive slots of the same (row, head, kv)
+  __host__ __device__ __forceinline__ size_t offset(int layer, int kv, int row, int head, int slot) const {
+    return (((((static_cast<size_t>(layer) * rows_cap + row) * 16 + head) * slots_cap + slot) * 2) + kv) * 64;
   }
 };
 

@@ -59,17 +59,17 @@ def test_logits_teacher_forced_at_real_cache_lengths(eng, golden):
         _check_steps(logits, g, range(lo, hi))
 
 
-@pytest.mark.parametrize("opts", [dict(fused_attn=0), dict(attn_alg=2), dict(attn_alg=1, attn_warps=8, attn_slots=4), dict(cuda_graph=0)])
+@pytest.mark.parametrize("opts", [dict(fused_attn=0), dict(attn_early=1), dict(attn_warps=8, attn_slots=4), dict(cuda_graph=0)])
 def test_logits_teacher_forced_decode_variants(eng, golden, opts):
     g = golden("lm_long.npz")
     feats, ids = T(g["feats"]).cuda(), T(g["ids"]).cuda()
     try:
         for k, v in opts.items():
             eng.set_option(k, v)
-        logits = eng.lm_forced_logits(feats, ids[:, :70].contiguous())  # cache length up to 71: three 32-key chunks
+        logits = eng.lm_forced_logits(feats, ids[:, :70].contiguous())  # cache length up to 71: five 16-key chunks
         _check_steps(logits, g, range(70))
     finally:
-        for k, v in dict(fused_attn=1, attn_alg=1, attn_warps=16, attn_slots=2, cuda_graph=1).items():
+        for k, v in dict(fused_attn=1, attn_early=0, attn_warps=16, attn_slots=2, cuda_graph=1).items():
             eng.set_option(k, v)
 
 

@@ -39,13 +39,17 @@ print("  gemm_2cta=0                       : %.3f ms" % run(0, gemm_2cta=0), flu
 eng.set_option("gemm_2cta", 1)
 print("  attn_balance=0 (128-row tiles)    : %.3f ms" % run(0, attn_balance=0), flush=True)
 eng.set_option("attn_balance", 1)
+print("  attn_early=1                      : %.3f ms" % run(0, attn_early=1), flush=True)
+eng.set_option("attn_early", 0)
+print("  epi_tma=0 (register epilogue)     : %.3f ms" % run(0, epi_tma=0), flush=True)
+eng.set_option("epi_tma", 1)
 if "variants" in sys.argv:
     print("  dual=1 (two halves out of phase)  : %.3f ms" % run(0, dual=1), flush=True)
     eng.set_option("dual", 0)
 if "variants" in sys.argv:
-    for alg, aw, sl in ((2, 16, 2), (1, 16, 2)):
-        print("  attn_alg=%d attn_warps=%d attn_slots=%d : %.3f ms" % (alg, aw, sl, run(0, attn_alg=alg, attn_warps=aw, attn_slots=sl)), flush=True)
-    print("  l2_ahead=2 (attn_alg 1, 16/2)     : %.3f ms" % run(0, l2_ahead=2), flush=True)
+    for aw, sl in ((8, 4), (24, 1), (16, 2)):
+        print("  attn_warps=%d attn_slots=%d        : %.3f ms" % (aw, sl, run(0, attn_warps=aw, attn_slots=sl)), flush=True)
+    print("  l2_ahead=2 (16 warps x 2 slots)   : %.3f ms" % run(0, l2_ahead=2), flush=True)
     eng.set_option("l2_ahead", 0)
     print("  fused_attn=0 (round 1 step)       : %.3f ms" % run(0, fused_attn=0), flush=True)
     eng.set_option("fused_attn", 1)
