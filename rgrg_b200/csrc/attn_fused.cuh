@@ -5,9 +5,10 @@
 // Tiling is head-aligned: CTA (m, h) computes the 128 x 192 tile [q_h | k_h | v_h] of M tile m — the three 64-row groups
 // of the c_attn weight that belong to head h are fetched by three TMA boxes into one 192-row operand B — so everything
 // the attention of (row, head h) needs is produced by the CTA that consumes it:
-//   1. tcgen05 main loop (K = 1024: 16 k-blocks, accumulator 128 x 192 fp32 in TMEM), fed by TMA through a 3-stage ring;
-//   2. epilogue: + bias -> bf16; q / k_new / v_new -> swizzled shared-memory tiles; k_new, v_new appended in place into
-//      the KV cache at slot t+1 (the reference regrows the cache with torch.cat, language_model.py:169-170);
+//   1. tcgen05 main loop (K = 1024: 16 k-blocks, accumulator 128 x 192 fp32 in TMEM), fed by TMA through a 4-stage ring;
+//   2. epilogue: + bias -> bf16; q / k_new / v_new -> swizzled shared-memory tiles (k_new, v_new are appended in place into
+//      the KV cache at slot t+1 by the attention warps, one 256-byte store per item; the reference regrows the cache with
+//      torch.cat, language_model.py:169-170);
 //   3. attention: AW warps, one (row, head) item per warp at a time; the cached keys / values of an item (slots 0..t: ONE
 //      contiguous block of L x 256 B, key row and value row of a slot adjacent) are streamed in 16-key chunks, one
 //      cp.async.bulk per chunk, into a per-warp ring of NSLOT shared-memory slots (mbarrier complete_tx); the new key /
@@ -32,7 +33,12 @@ namespace rgrg {
 namespace fa {
 
 constexpr int BN = 192;      // q | k | v columns of one head
-constexpr int STAGES = 3;    // 16 k-blocks only: a short ring is enough
+#ifndef RGRG_FA_STAGES
+#define RGRG_FA_STAGES 4
+#endif
+// TMA ring depth of the c_attn phase (16 k-blocks).  Measured step at 928 rows: 3 stages 2.013 ms, 4 stages 1.985, 5 stages 1.990;
+// 4 x 40 KB still fits under the attention phase's footprint (48 KB of tiles + 128 KB of staging rings), which aliases it.
+constexpr int STAGES = RGRG_FA_STAGES;
 constexpr int A_BYTES = tc::BM * tc::BK * 2;   // 16 KB
 constexpr int B_BYTES = BN * tc::BK * 2;       // 24 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -70,6 +76,7 @@ struct Params {
   int M;
   int rows_per_tile;     // rows OWNED by one M tile (<= 128; the MMA still covers 128 rows, the surplus belongs to the next tile):
                          // rows are spread evenly over as many tiles as there are SMs / 16, so every CTA streams the same amount
+  int mc;                // 1: head pairs share operand A by TMA multicast (cluster of 2; needs the 64-row map)
   int early_kv;          // 1: the first K / V chunks are requested before the epilogue instead of after it
   int l2_ahead;          // items whose K / V blocks are prefetched into L2 ahead of the consumer (0 = off; measured: no gain —
                          // neither this nor prefetching the NEXT layer's cache during the GEMM kernels, profiles/r02_decode.md)
@@ -95,6 +102,29 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
 }
+// A-operand sharing between the two heads of a CTA pair (Params::mc): each CTA fetches 64 of the 128 rows and multicasts
+// them into both CTAs' rings; the bytes are credited to the full barrier at the same offset in both CTAs
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          tc::smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// "these MMAs have read their operands": arrives on the barrier at this offset in every CTA of the mask
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   tc::smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -102,6 +132,7 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 
 template <int AW, int NSLOT, bool LN_HEAD, int ALG>
 __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                        const __grid_constant__ CUtensorMap tmA64,
                                                                         const __grid_constant__ CUtensorMap tmW, const Params p) {
   using L = Smem<AW, NSLOT, ALG>;
   constexpr int ATT_WARPS = AW;
@@ -115,6 +146,9 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) trace_mark(p.trace, 0);
   const int head = blockIdx.x & 15, m_blk = blockIdx.x >> 4;  // the 16 heads of an M tile are consecutive CTAs (one cluster)
+  // mc: CTAs (2i, 2i + 1) — two heads of the same M tile — form a cluster and share operand A through TMA multicast
+  const bool mc = !LN_HEAD && p.mc;
+  const uint32_t rank = mc ? cluster_ctarank() : 0;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmA);
@@ -122,7 +156,7 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
 #pragma unroll
     for (int i = 0; i < STAGES; ++i) {
       tc::mbar_init(&full_bar[i], 1);
-      tc::mbar_init(&empty_bar[i], 1);
+      tc::mbar_init(&empty_bar[i], mc ? 2 : 1);  // mc: a ring slot is written by both CTAs, so both MMA issuers release it
     }
     tc::mbar_init(tmem_full_bar, 1);
     for (int i = 0; i < ATT_WARPS * NSLOT; ++i) tc::mbar_init(&att_bar[i], 1);
@@ -134,6 +168,10 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (mc) {  // the peer's barriers must be initialised before anything of ours can signal them
+    cluster_arrive();
+    cluster_wait();
+  }
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   griddep_launch_dependents();  // dependents may be scheduled; they block at their own griddep_wait until this grid completes
@@ -183,7 +221,10 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
           for (int j = 0; j < 3; ++j)
             tc::tma_load_2d(a_dst + A_BYTES + j * 64 * 128, &tmW, &full_bar[st], kb * tc::BK, j * 1024 + head * 64);
         }
-        tc::tma_load_2d(a_dst, &tmA, &full_bar[st], kb * tc::BK, m_blk * p.rows_per_tile);
+        if (mc)  // rows [64 rank, +64) of the tile, into both CTAs' slots
+          tma_load_2d_mc(a_dst + rank * (A_BYTES / 2), &tmA64, &full_bar[st], kb * tc::BK, m_blk * p.rows_per_tile + static_cast<int>(rank) * 64, 3);
+        else
+          tc::tma_load_2d(a_dst, &tmA, &full_bar[st], kb * tc::BK, m_blk * p.rows_per_tile);
       }
     }
   } else if (warp == 1) {
@@ -199,7 +240,8 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
         const uint64_t b_desc = tc::make_sw128_kmajor_desc(a_addr + A_BYTES);
 #pragma unroll
         for (int k = 0; k < tc::BK / tc::UMMA_K; ++k) tc::umma_bf16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-        tc::umma_commit(&empty_bar[st]);
+        if (mc) umma_commit_mc(&empty_bar[st], 3);
+        else tc::umma_commit(&empty_bar[st]);
       }
       tc::umma_commit(tmem_full_bar);
     }
@@ -247,10 +289,7 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
       const int q4 = warp & 3;           // TMEM lane quarter this warp may read
       const int grp = aw >> 2;           // which of the AW / 4 warps of that quarter: takes 16-column chunks grp, grp + AW/4, ...
       const int r = q4 * 32 + lane;      // local row
-      const int row = row0 + r;
-      const bool row_ok = r < rows_left;
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
-      const int slot = t + 1;
 #pragma unroll 1
       for (int c = grp * 16; c < BN; c += 4 * AW) {
         uint32_t v[16];
@@ -266,11 +305,6 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
         const int ch = cc >> 3;  // 16-byte chunk index within the 128-byte row
         *reinterpret_cast<uint4*>(tile_row + ((ch ^ (r & 7)) << 4)) = lo;
         *reinterpret_cast<uint4*>(tile_row + (((ch + 1) ^ (r & 7)) << 4)) = hi;
-        if (which >= 1 && row_ok) {
-          bf16* dst = p.kv.cache + p.kv.offset(p.layer, which - 1, row, head, slot) + cc;
-          *reinterpret_cast<uint4*>(dst) = lo;
-          *reinterpret_cast<uint4*>(dst + 8) = hi;
-        }
       }
       tc::tc_fence_before();
     }
@@ -294,6 +328,10 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
         unpack8(*reinterpret_cast<const uint4*>(smem + rl * 128 + sw), qv);
         const uint4 knew = *reinterpret_cast<const uint4*>(smem + TILE_BYTES + rl * 128 + sw);
         const uint4 vnew = *reinterpret_cast<const uint4*>(smem + 2 * TILE_BYTES + rl * 128 + sw);
+        // KV-cache append of this item (slot t + 1): key row and value row are adjacent, so 16 lanes write one contiguous 256-byte
+        // block — off the epilogue's critical path, where it was 32 scattered 16-byte stores per warp instruction
+        if (sub < 2)
+          *reinterpret_cast<uint4*>(p.kv.cache + p.kv.offset(p.layer, sub, item_row(j), head, t + 1) + dseg * 8) = sub == 0 ? knew : vnew;
         float m = -INFINITY, den = 0.0f;
         float acc[8];
   #pragma unroll
@@ -378,12 +416,17 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
   if (warp == 2 && lane == 0) trace_mark(p.trace, 6);
   tc::tc_fence_before();
   __syncthreads();
+  if (mc) {  // no CTA of the pair exits while the other may still signal its barriers
+    cluster_arrive();
+    cluster_wait();
+  }
   if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
   if (threadIdx.x == 0) trace_mark(p.trace, 7);
 }
 
 template <int AW, int NSLOT, bool LN_HEAD, int ALG>
-inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const Params& p, cudaStream_t stream, bool pdl) {
+inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmA64, const CUtensorMap& tmW, const Params& p, cudaStream_t stream,
+                   bool pdl) {
   using L = Smem<AW, NSLOT, ALG>;
   auto kern = attn_fused_kernel<AW, NSLOT, LN_HEAD, ALG>;
   static bool configured = false;  // one engine device per process (rgrg_create enforces it)
@@ -403,9 +446,16 @@ inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmW, const Params&
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
   }
+  if (!LN_HEAD && p.mc) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = 2;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
   cfg.attrs = attr;
   cfg.numAttrs = n;
-  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmW, p));
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmA64, tmW, p));
 }
 
 }  // namespace fa

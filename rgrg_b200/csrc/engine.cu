@@ -249,6 +249,7 @@ struct rgrg_engine {
   }
   int opt_attn_balance = 1;     // fused attention: rows spread evenly over (#SMs / 16) M tiles instead of 128-row tiles
   int opt_gemm_2cta_waves = 2;  // the pair kernel is used while its grid fits in this many waves (else the persistent 1-CTA kernel)
+  int opt_attn_mc = 0;          // fused attention: head pairs (clusters of 2) share operand A through TMA multicast
   int opt_attn_early = 0;       // fused attention: request the first K / V chunks before the epilogue
   int opt_epi_tma = 1;          // CTA-pair kernel: plain epilogues leave through shared-memory slabs + TMA stores
   int opt_gemm_2cta_stages = 6; // its TMA ring depth: 6 (one CTA per SM) / 4 / 3 (two CTAs per SM: prologue overlaps the predecessor's epilogue)
@@ -1305,11 +1306,11 @@ struct rgrg_engine {
 
   // (attention warps, ring slots per warp): 48 KB of q/k/v tiles + AW * NSLOT * 4 KB of K/V staging must fit in 227 KB
   template <bool LN_HEAD>
-  void launch_attn_fused(const CUtensorMap& tmA, const CUtensorMap& tmW, const fa::Params& fp, cudaStream_t st) {
+  void launch_attn_fused(const CUtensorMap& tmA, const CUtensorMap& tmA64, const CUtensorMap& tmW, const fa::Params& fp, cudaStream_t st) {
     switch (opt_attn_warps * 10 + opt_attn_slots) {
-      case 84: fa::launch<8, 4, LN_HEAD, 1>(tmA, tmW, fp, st, pdl_now); break;
-      case 162: fa::launch<16, 2, LN_HEAD, 1>(tmA, tmW, fp, st, pdl_now); break;
-      case 241: fa::launch<24, 1, LN_HEAD, 1>(tmA, tmW, fp, st, pdl_now); break;
+      case 84: fa::launch<8, 4, LN_HEAD, 1>(tmA, tmA64, tmW, fp, st, pdl_now); break;
+      case 162: fa::launch<16, 2, LN_HEAD, 1>(tmA, tmA64, tmW, fp, st, pdl_now); break;
+      case 241: fa::launch<24, 1, LN_HEAD, 1>(tmA, tmA64, tmW, fp, st, pdl_now); break;
       default: throw std::runtime_error("unsupported (attn_warps, attn_slots)");
     }
   }
@@ -1332,7 +1333,7 @@ struct rgrg_engine {
     const int* ids;  // first row of the view
     int ids_ld;
     unsigned* counters;  // LayerNorm-head counters of this view
-    CUtensorMap tm_x;
+    CUtensorMap tm_x, tm_x64;  // operand A of the GEMMs: 128-row boxes; 64-row boxes for the multicast halves of attn_fused
     const float* pending_bias;  // bias of the split-K projection whose partial sums wait in `parts`
   };
   DecView dec_view(int row0, int rows, const int* ids_all, int ids_ld) {
@@ -1352,6 +1353,7 @@ struct rgrg_engine {
     v.ids_ld = ids_ld;
     v.counters = ln_counters.as<unsigned>() + (row0 ? 256 : 0);
     v.tm_x = tc::make_tmap_2d(v.x, rows, DM, 128);
+    v.tm_x64 = tc::make_tmap_2d(v.x, rows, DM, 64);
     v.pending_bias = nullptr;
     return v;
   }
@@ -1402,6 +1404,7 @@ struct rgrg_engine {
       fp.l2_ahead = opt_l2_ahead;
       fp.trace = trace_ptr();
       fp.early_kv = opt_attn_early;
+      fp.mc = opt_attn_mc;
       if (head) {
         fp.h = v.h;
         fp.x = v.x;
@@ -1420,8 +1423,8 @@ struct rgrg_engine {
       before_attn();
       if (!(opt_ablate & 64)) {
         ProfScope ps(this, "attn_fused", st);
-        if (head) launch_attn_fused<true>(v.tm_x, L.attn.tm[0], fp, st);
-        else launch_attn_fused<false>(v.tm_x, L.attn.tm[0], fp, st);
+        if (head) launch_attn_fused<true>(v.tm_x, v.tm_x64, L.attn.tm[0], fp, st);
+        else launch_attn_fused<false>(v.tm_x, v.tm_x64, L.attn.tm[0], fp, st);
         ++launches;
       }
     } else {
@@ -2032,6 +2035,7 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "gemm_2cta_stages") e->opt_gemm_2cta_stages = value;
   else if (k == "epi_tma") e->opt_epi_tma = value;
   else if (k == "attn_early") e->opt_attn_early = value;
+  else if (k == "attn_mc") e->opt_attn_mc = value;
   else if (k == "gemm_2cta_waves") e->opt_gemm_2cta_waves = value;
   else if (k == "attn_balance") e->opt_attn_balance = value;
   else if (k == "trace") e->opt_trace = value;

@@ -261,6 +261,9 @@ def test_out_of_memory_is_recoverable(model, oracle_detail):
     assert eng.lm_generate(feats[:3], 9).shape == (3, 9)
 
 
+ATTN_MC_DEFAULT = 0  # engine default of attn_mc
+
+
 def _opts(eng, **kw):
     for k, v in kw.items():
         eng.set_option(k, v)
@@ -285,8 +288,15 @@ def test_fused_attention_is_bit_identical_to_two_kernel_attention(model, oracle_
         # first K / V chunks requested before the epilogue instead of after it: same bits
         _opts(eng, cuda_graph=1, attn_warps=16, attn_slots=2, l2_ahead=0, attn_early=1)
         assert np.array_equal(ref, eng.lm_generate(feats, 36))
+        # head pairs sharing operand A through TMA multicast (clusters of 2): same MMAs on the same bytes
+        for mc in (1, 0):  # set_option drops the step graph each time
+            _opts(eng, attn_early=0, attn_mc=mc)
+            assert np.array_equal(ref, eng.lm_generate(feats, 36)), "attn_mc=%d" % mc
+        _opts(eng, attn_mc=1, cuda_graph=0)
+        assert np.array_equal(ref, eng.lm_generate(feats, 36))
+        _opts(eng, cuda_graph=1)
     finally:
-        _opts(eng, cuda_graph=1, fused_attn=1, attn_early=0, attn_warps=16, attn_slots=2, l2_ahead=0, ln_head=0)
+        _opts(eng, cuda_graph=1, fused_attn=1, attn_early=0, attn_mc=ATTN_MC_DEFAULT, attn_warps=16, attn_slots=2, l2_ahead=0, ln_head=0)
 
 
 def test_layernorm_head_matches_separate_layernorm(model, oracle_detail):

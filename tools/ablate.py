@@ -41,6 +41,8 @@ print("  attn_balance=0 (128-row tiles)    : %.3f ms" % run(0, attn_balance=0), 
 eng.set_option("attn_balance", 1)
 print("  attn_early=1                      : %.3f ms" % run(0, attn_early=1), flush=True)
 eng.set_option("attn_early", 0)
+print("  attn_mc=1 (A multicast, head pairs): %.3f ms" % run(0, attn_mc=1), flush=True)
+print("  attn_mc=0                         : %.3f ms" % run(0, attn_mc=0), flush=True)
 print("  epi_tma=0 (register epilogue)     : %.3f ms" % run(0, epi_tma=0), flush=True)
 eng.set_option("epi_tma", 1)
 if "variants" in sys.argv:
