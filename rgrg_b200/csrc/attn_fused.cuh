@@ -3,7 +3,7 @@
 // SURVEY.md §2c).
 //
 // Tiling is head-aligned: CTA (m, h) computes the 128 x 192 tile [q_h | k_h | v_h] of M tile m — the three 64-row groups
-// of the c_attn weight that belong to head h are fetched by three TMA boxes into one 192-row operand B — so everything
+// of the c_attn weight that belong to head h are fetched by one 3-D TMA box into one 192-row operand B — so everything
 // the attention of (row, head h) needs is produced by the CTA that consumes it:
 //   1. tcgen05 main loop (K = 1024: 16 k-blocks, accumulator 128 x 192 fp32 in TMEM), fed by TMA through a 4-stage ring;
 //   2. epilogue: + bias -> bf16; q / k_new / v_new -> swizzled shared-memory tiles (k_new, v_new are appended in place into
@@ -102,6 +102,25 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
 }
+// c_attn weight viewed as [3 (q | k | v)][1024 rows][1024 K]: the three 64-row groups of one head in ONE request
+inline CUtensorMap make_tmap_qkv(const void* w) {
+  CUtensorMap m;
+  cuuint64_t dims[3] = {1024, 1024, 3};
+  cuuint64_t strides[2] = {1024 * 2, 1024ull * 1024 * 2};
+  cuuint32_t box[3] = {tc::BK, 64, 3};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = tc::encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(qkv) failed: " + std::to_string((int)r));
+  return m;
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                   tc::smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(tc::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 // A-operand sharing between the two heads of a CTA pair (Params::mc): each CTA fetches 64 of the 128 rows and multicasts
 // them into both CTAs' rings; the bytes are credited to the full barrier at the same offset in both CTAs
 __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
@@ -182,9 +201,7 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
 #pragma unroll
     for (int i = 0; i < STAGES; ++i) {
       tc::mbar_expect_tx(&full_bar[i], STAGE_BYTES);
-      uint8_t* b_dst = smem + i * STAGE_BYTES + A_BYTES;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) tc::tma_load_2d(b_dst + j * 64 * 128, &tmW, &full_bar[i], i * tc::BK, j * 1024 + head * 64);
+      tma_load_3d(smem + i * STAGE_BYTES + A_BYTES, &tmW, &full_bar[i], i * tc::BK, head * 64, 0);
     }
   }
   griddep_wait();
@@ -217,9 +234,7 @@ __global__ void __launch_bounds__(64 + 32 * AW, 1) attn_fused_kernel(const __gri
         if (kb >= STAGES) {
           tc::mbar_wait(&empty_bar[st], ((kb / STAGES) & 1) ^ 1);
           tc::mbar_expect_tx(&full_bar[st], STAGE_BYTES);
-#pragma unroll
-          for (int j = 0; j < 3; ++j)
-            tc::tma_load_2d(a_dst + A_BYTES + j * 64 * 128, &tmW, &full_bar[st], kb * tc::BK, j * 1024 + head * 64);
+          tma_load_3d(a_dst + A_BYTES, &tmW, &full_bar[st], kb * tc::BK, head * 64, 0);
         }
         if (mc)  // rows [64 rank, +64) of the tile, into both CTAs' slots
           tma_load_2d_mc(a_dst + rank * (A_BYTES / 2), &tmA64, &full_bar[st], kb * tc::BK, m_blk * p.rows_per_tile + static_cast<int>(rank) * 64, 3);

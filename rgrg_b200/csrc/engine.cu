@@ -98,6 +98,7 @@ struct BlockW {
 struct LayerW {
   float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
   Linear attn, proj, fc, mproj;
+  CUtensorMap tm_qkv;  // c_attn weight as [3][1024][1024]: q | k | v rows of one head in one box (attn_fused.cuh)
 };
 
 }  // namespace
@@ -795,6 +796,8 @@ struct rgrg_engine {
       L.ln2_g = upload_keep(need(p + ".2.weight"));
       L.ln2_b = upload_keep(need(p + ".2.bias"));
       L.attn = make_conv1d(p + ".1.c_attn");
+      if (L.attn.N != 3 * DM || L.attn.K != DM) throw std::runtime_error("c_attn must be [1024, 3072]");
+      L.tm_qkv = fa::make_tmap_qkv(L.attn.w);
       L.proj = make_conv1d(p + ".1.c_proj");
       L.fc = make_conv1d(p + ".3.c_fc");
       L.mproj = make_conv1d(p + ".3.c_proj");
@@ -1423,8 +1426,8 @@ struct rgrg_engine {
       before_attn();
       if (!(opt_ablate & 64)) {
         ProfScope ps(this, "attn_fused", st);
-        if (head) launch_attn_fused<true>(v.tm_x, v.tm_x64, L.attn.tm[0], fp, st);
-        else launch_attn_fused<false>(v.tm_x, v.tm_x64, L.attn.tm[0], fp, st);
+        if (head) launch_attn_fused<true>(v.tm_x, v.tm_x64, L.tm_qkv, fp, st);
+        else launch_attn_fused<false>(v.tm_x, v.tm_x64, L.tm_qkv, fp, st);
         ++launches;
       }
     } else {

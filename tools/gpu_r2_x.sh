@@ -1,13 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_path.py tests/test_gpu_decoder_parity.py -m gpu -q --timeout 500 -x 2>&1 | tail -4
-timeout 600 python tools/ablate.py 2>&1 | grep -E "full step|without attn_fused"
+timeout 600 python tools/ablate.py 2>&1 | grep -E "full step|without attn_fused|attn_mc"
 T=48 timeout 600 python tools/decode_timeline.py 2>&1 | grep -A2 "^layer 12"
-cp rgrg_b200/librgrg_b200.so /tmp/lib_s3.so
-for st in 4 5; do
-  cp build_variants/lib_s$st.so rgrg_b200/librgrg_b200.so
-  echo "=== ring depth $st"
-  timeout 600 python tools/ablate.py 2>&1 | grep -E "full step|without attn_fused"
-  T=48 timeout 600 python tools/decode_timeline.py 2>&1 | grep -A2 "^layer 12"
-done
-cp /tmp/lib_s3.so rgrg_b200/librgrg_b200.so
