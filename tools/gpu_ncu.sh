@@ -1,5 +1,5 @@
 #!/bin/bash
-# full GPU suite, then ncu --set full of the CTA-pair projections (TMA-store epilogue) and of the fused attention kernel at cache
+# ncu --set full of the CTA-pair projections (TMA-store epilogue) and of the fused attention kernel at cache
 # length ~58; reports are converted to CSV on the box (gpurun brings back at most 64 MiB)
 mkdir -p gpurun_out
 
