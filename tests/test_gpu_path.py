@@ -322,11 +322,11 @@ def test_layernorm_head_matches_separate_layernorm(model, oracle_detail):
 
 def test_cta_pair_projections_are_bit_identical(model, oracle_detail):
     """Decode projections through the CTA-pair kernel vs the 1-CTA kernel: same k order and fp32 accumulation, so tokens
-    are identical (full M tiles, a partial last tile, an odd tile count)."""
+    are identical (full M tiles, a partial last tile, an odd tile count, more pairs than one wave)."""
     eng = model._engine()
-    feats = torch.cat([oracle_detail["sel_feats"]] * 7, 0).contiguous().cuda()  # 406 rows
+    feats = torch.cat([oracle_detail["sel_feats"]] * 21, 0).contiguous().cuda()  # 1218 rows
     try:
-        for rows in (406, 290, 60):
+        for rows in (406, 290, 60, 1218):  # 1218 rows: two waves of CTA pairs (gemm_2cta_waves = 2)
             _opts(eng, gemm_2cta=0)
             a = eng.lm_generate(feats[:rows], 16)
             _opts(eng, gemm_2cta=1)
