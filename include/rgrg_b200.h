@@ -176,11 +176,19 @@ RGRG_API int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst,
  *   "pdl" (0/1)               programmatic dependent launch between the kernels of a decode step
  *   "fused_attn" (0/1)        greedy decode: c_attn + KV append + attention as one head-aligned kernel (attn_fused.cuh);
  *                             0 = c_attn GEMM (KV-append epilogue) + stand-alone attention kernel (always used by beam search)
- *   "gemm_2cta" (0/1)         decode projections through the CTA-pair kernel (256 x 256 tiles, each CTA stages half of W)
+ *   "gemm_2cta" (0/1)         decode projections through the CTA-pair kernel (256 x 256 tiles, each CTA stages half of W);
+ *                             "gemm_2cta_waves" (1/2): used while the pair grid fits in this many waves (default 2)
+ *   "epi_tma" (0/1)           CTA-pair kernel: plain epilogues leave through shared-memory slabs + TMA stores (1, default) or
+ *                             through registers and 16-byte global stores (0); bit-identical
+ *   "attn_mc", "attn_early" (0/1)  fused attention: operand A shared between head pairs by TMA multicast / first K,V chunks
+ *                             requested before the epilogue (both bit-identical, measured without gain, default 0)
+ *   "trace" (0/1)             tuning only: %globaltimer stamps of the first / last CTA of the decode kernels
+ *                             (tools/decode_timeline.py)
  *   "dual" (0/1)              greedy decode step as two row halves half a layer out of phase (measured slower)
  *   "ln_head" (0/1)           LayerNorm (+ split-K reduce + residual) as the 16-CTA-cluster head of the consumer GEMM;
  *                             0 = separate LayerNorm kernels
- *   "attn_slots" (3/4/5)      fused attention: K/V ring slots per warp;  "l2_ahead" (n): items prefetched into L2
+ *   "attn_warps" / "attn_slots" (16/2, 8/4, 24/1)   fused attention: warps per CTA and K/V ring slots per warp;
+ *                             "l2_ahead" (n): items prefetched into L2
  *   "attn_occ" (5..8), "cattn_bn" (0/128/192/256)   tuning of the two-kernel attention path
  *   "implicit_conv" (0/1)     3x3 convs as TMA implicit GEMM (1) or im2col + GEMM (0)
  *   "gemm_impl" (0/2)         0 tcgen05, 2 CUDA-core cross-check of every bf16 GEMM
