@@ -73,6 +73,11 @@ struct TmaOutOk : std::false_type {};
 template <class E>
 struct TmaOutOk<E, std::void_t<decltype(E::kTmaOut)>> : std::bool_constant<E::kTmaOut> {};
 
+template <class E, class = void>
+struct TmaOutRowOk : std::false_type {};
+template <class E>
+struct TmaOutRowOk<E, std::void_t<decltype(E::kTmaOutRow)>> : std::bool_constant<E::kTmaOutRow> {};
+
 struct Linear {
   bf16* w = nullptr;
   float* bias = nullptr;
@@ -484,6 +489,15 @@ struct rgrg_engine {
   }
   template <class Epi>
   void launch_bn(int bn, const CUtensorMap& tmA, const Linear& W, const tc::GemmShape& s, const Epi& epi, cudaStream_t st) {
+    // plain GEMMs with a bf16 output (1x1 convolutions, fc6 / fc7): TMA-store epilogue (gemm_tc.cuh)
+    if constexpr (TmaOutRowOk<Epi>::value) {
+      if (opt_epi_tma && !s.conv && s.k_splits <= 1 && (bn == 128 || bn == 256) && epi.ldc == s.N && s.N % 64 == 0) {
+        const CUtensorMap tmC = tc::make_tmap_out_bf16(epi.out, s.M, s.N);
+        if (bn == 128) tc::launch<128, 6, Epi, false, true>(tmA, W.tm[1], s, epi, st, pdl_now, &tmC);
+        else tc::launch<256, 4, Epi, false, true>(tmA, W.tm[3], s, epi, st, pdl_now, &tmC);
+        return;
+      }
+    }
     switch (bn) {
       case 64: tc::launch<64, 8, Epi>(tmA, W.tm[0], s, epi, st, pdl_now); break;
       case 128: tc::launch<128, 6, Epi>(tmA, W.tm[1], s, epi, st, pdl_now); break;

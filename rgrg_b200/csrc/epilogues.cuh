@@ -58,6 +58,31 @@ struct EpiStoreT {
     }
   }
 
+  // the same with the bf16 residual of a full-width row segment added between bias and activation (the order of apply());
+  // for the persistent kernel's TMA-store epilogue (gemm_tc.cuh), bf16 outputs only
+  static constexpr bool kTmaOutRow = OUT_BF16 && (RES == RES_NONE || RES == RES_BF16);
+  template <int NV>
+  __device__ __forceinline__ void transform_row(int row, bool row_ok, int col0, float* o) const {
+    if constexpr (BIAS) add_vec_f32<NV>(o, bias + col0);
+    if constexpr (RES == RES_BF16) {
+      if (row_ok) {
+        const bf16* rp = static_cast<const bf16*>(res) + static_cast<size_t>(row) * ldc + col0;
+#pragma unroll
+        for (int j = 0; j < NV; j += 8) {
+          float r[8];
+          unpack8(*reinterpret_cast<const uint4*>(rp + j), r);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[j + k] += r[k];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      if constexpr (ACT == ACT_RELU) o[j] = fmaxf(o[j], 0.0f);
+      if constexpr (ACT == ACT_GELU_NEW) o[j] = gelu_new(o[j]);
+    }
+  }
+
   template <int NV>
   __device__ __forceinline__ void apply(State& st, int row, int col0, const float* v, int N) const {
     const size_t base = static_cast<size_t>(row) * ldc + col0 + st.split_off;

@@ -191,7 +191,11 @@ struct SmemLayout {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STG_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STG_BYTES = EPI_WARPS * STG_FLOATS * 4;
+  // per-warp staging: 2 KB transpose buffers (register epilogue); BN = 128 / 256 keep 4 KB per warp so that the TMA-store epilogue
+  // (32-row x 128-byte slabs) fits as well — their rings are 192 KB, the other widths have no room for it
+  static constexpr int SLAB_BYTES = 32 * 128;
+  static constexpr bool kSlabs = (BN == 128 || BN == 256);
+  static constexpr int STG_BYTES = EPI_WARPS * (kSlabs ? SLAB_BYTES : STG_FLOATS * 4);
   static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
   static_assert(TOTAL <= 232448, "shared memory budget exceeded");
@@ -371,12 +375,13 @@ struct Pipe {
   }
 
   // epilogue main loop (warps 2..9, all lanes)
-  template <class Epi>
-  __device__ __forceinline__ void epilogue(const GemmShape& s, const Epi& epi, int& it, long long* trace) const {
+  template <class Epi, bool TMA_OUT>
+  __device__ __forceinline__ void epilogue(const GemmShape& s, const Epi& epi, int& it, long long* trace, const CUtensorMap* tmC) const {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3;            // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
     const int half = (warp - 2) >> 2;  // which of the two warps of that quarter: takes 16-column chunks half, half+2, ...
     float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET) + (warp - 2) * STG_FLOATS;
+    uint8_t* slab = smem + L::STG_OFFSET + (warp - 2) * L::SLAB_BYTES;  // TMA_OUT: this warp's 32-row x 128-byte store slab
     const int nt = num_tiles(s);
     for (int tile = blockIdx.x; tile < nt; tile += gridDim.x, ++it) {
       const TileCoord tc_ = tile_coord(s, tile);
@@ -405,6 +410,55 @@ struct Pipe {
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         if (row_ok) epi.finish(st, row, tc_.n_blk * 2 + half);
+      } else if constexpr (TMA_OUT) {
+        // Plain GEMM, bf16 output (optionally + bf16 residual): TMEM -> registers (lane = row) -> bias / residual / activation ->
+        // bf16 -> the warp's 128B-swizzled slab -> one cp.async.bulk.tensor store per 32 rows x 64 columns.  The register
+        // epilogue below issues 16 rows x 32 B per warp store instruction and is bound by store issue on the K <= 512
+        // convolutions (tensor pipe 2-8 % busy, profiles/r02_detector_gemms_ncu_full.md); rows past M and columns past N are
+        // clipped by the TMA unit.
+        constexpr int COLS = BN / 2;        // two warps per TMEM lane quarter, half of the tile's columns each
+        constexpr int SLABS = COLS / 64;
+        static_assert(L::kSlabs && COLS % 64 == 0, "TMA-store epilogue needs BN = 128 or 256");
+        const int r = q * 32 + lane;
+        const int row = tc_.m_blk * BM + r;
+        const bool row_ok = row < s.M;
+        const int m0 = tc_.m_blk * BM + q * 32;
+        const int sw = lane & 7;
+#pragma unroll 1
+        for (int b = 0; b < SLABS; ++b) {
+          const int cs = tc_.n_blk * BN + half * COLS + b * 64;  // first output column of this slab
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the slab's previous store has read it
+          __syncwarp();
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int c = half * COLS + b * 64 + h2 * 32;
+            uint32_t v[32];
+            tmem_ld_32x32b_x16(t_addr + c, v);
+            tmem_ld_32x32b_x16(t_addr + c + 16, v + 16);
+            tmem_ld_wait();
+            if (b == SLABS - 1 && h2 == 1) {  // this warp's last read of the accumulator stage: hand it back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            }
+            if (cs < s.N) {
+              float o[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+              epi.template transform_row<32>(row, row_ok, cs + h2 * 32, o);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(slab + lane * 128 + (((h2 * 4 + j) ^ sw) << 4)) = pack8(o + 8 * j);
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0 && m0 < s.M && cs < s.N) {
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmC)),
+                         "r"(smem_u32(slab)), "r"(cs), "r"(m0)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
       } else {
         // rows of the two transposed passes this lane stores: lane>>1 and 16 + lane>>1 of the warp's 32
         int rows[2];
@@ -455,6 +509,9 @@ struct Pipe {
         }
       }
     }
+    if constexpr (TMA_OUT) {
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory must outlive the stores' reads
+    }
   }
 };
 
@@ -462,9 +519,10 @@ struct Pipe {
 __device__ __forceinline__ void ln_head_row(float* h, const float* gamma, const float* beta, bf16* x, int row, int lane,
                                             const float* parts, size_t part_stride, const float* res_bias);
 
-template <int BN, int STAGES, class Epi, bool LN_HEAD = false>
+template <int BN, int STAGES, class Epi, bool LN_HEAD = false, bool TMA_OUT = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
+                                                               const __grid_constant__ CUtensorMap tmC,
                                                                const GemmShape s, const Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5;
@@ -500,7 +558,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   } else if (warp == 1) {
     if (lane == 0) pipe.mma(s, kbg, it, trace);
   } else {
-    pipe.epilogue(s, epi, it, trace);
+    pipe.template epilogue<Epi, TMA_OUT>(s, epi, it, trace, &tmC);
   }
   if (trace && warp == 2 && lane == 0) trace[5] = clock64();
   pipe.teardown();
@@ -563,11 +621,12 @@ inline int num_sms() {
   return n;
 }
 
-template <int BN, int STAGES, class Epi, bool LN_HEAD = false>
+template <int BN, int STAGES, class Epi, bool LN_HEAD = false, bool TMA_OUT = false>
 inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const Epi& epi,
-                   cudaStream_t stream, bool pdl = false) {
+                   cudaStream_t stream, bool pdl = false, const CUtensorMap* tmC = nullptr) {
   using L = SmemLayout<BN, STAGES>;
-  auto kern = gemm_tc_kernel<BN, STAGES, Epi, LN_HEAD>;
+  auto kern = gemm_tc_kernel<BN, STAGES, Epi, LN_HEAD, TMA_OUT>;
+  if (TMA_OUT && !tmC) throw std::runtime_error("TMA-store epilogue needs the output tensor map");
   constexpr int cluster = 1;
   static bool configured = false;  // one static per template instantiation; one engine device per process (rgrg_create)
   if (!configured) {
@@ -599,7 +658,21 @@ inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmSha
   }
   cfg.attrs = attr;
   cfg.numAttrs = n;
-  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, s, epi));
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC ? *tmC : tmA, s, epi));
+}
+
+// output map of the TMA-store epilogue: row-major bf16 [M, N]; slabs of 32 rows x 64 columns, 128B swizzle
+inline CUtensorMap make_tmap_out_bf16(const void* ptr, uint64_t M, uint64_t N) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {N, M};
+  cuuint64_t strides[1] = {N * 2};
+  cuuint32_t box[2] = {64, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(out bf16) failed: " + std::to_string((int)r));
+  return m;
 }
 
 }  // namespace tc

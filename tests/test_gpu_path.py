@@ -48,6 +48,28 @@ def test_backbone_features_within_bf16_tolerance(model, images, oracle_detail):
     assert _rel(feats, oracle_detail["features"]) < 0.05  # 53 chained bf16 convs (~4 %)
 
 
+def test_tma_store_epilogue_of_the_persistent_gemm_is_bit_identical(model, images):
+    """1x1 convolutions, fc6 and fc7 (plain GEMMs with a bf16 output, with and without a bf16 residual) leave through
+    shared-memory slabs + TMA stores by default; `epi_tma=0` is the register epilogue: same arithmetic in the same order, so
+    the backbone features, the fc7 activations and every detector output are identical bit for bit."""
+    eng = model._engine()
+    x = images.cuda()
+    try:
+        a = eng.backbone(x)
+        da = eng.detect(x)
+        fa = eng.debug_read("fc7", (64, 1024), np.uint16)
+        eng.set_option("epi_tma", 0)
+        b = eng.backbone(x)
+        db = eng.detect(x)
+        fb = eng.debug_read("fc7", (64, 1024), np.uint16)
+    finally:
+        eng.set_option("epi_tma", 1)
+    assert torch.equal(a, b)
+    assert np.array_equal(fa, fb)
+    for k in ("selected", "detected", "boxes", "scores", "region_features", "top_idx", "num_proposals"):
+        assert np.array_equal(da[k], db[k]), k
+
+
 def _oracle_class_scores(synth_sd, oracle_detail, b, boxes):
     """The oracle's 29 per-class scores (softmax over 30, background dropped) of arbitrary boxes of image b."""
     with torch.no_grad():
