@@ -493,8 +493,10 @@ struct rgrg_engine {
     if constexpr (TmaOutRowOk<Epi>::value) {
       if (opt_epi_tma && !s.conv && s.k_splits <= 1 && (bn == 128 || bn == 256) && epi.ldc == s.N && s.N % 64 == 0) {
         const CUtensorMap tmC = tc::make_tmap_out_bf16(epi.out, s.M, s.N);
-        if (bn == 128) tc::launch<128, 6, Epi, false, true>(tmA, W.tm[1], s, epi, st, pdl_now, &tmC);
-        else tc::launch<256, 4, Epi, false, true>(tmA, W.tm[3], s, epi, st, pdl_now, &tmC);
+        CUtensorMap tmR = tmC;  // the bf16 residual, if any, comes in through the same boxes
+        if constexpr (Epi::kResBf16) tmR = tc::make_tmap_out_bf16(epi.res, s.M, s.N);
+        if (bn == 128) tc::launch<128, 6, Epi, false, true>(tmA, W.tm[1], s, epi, st, pdl_now, &tmC, &tmR);
+        else tc::launch<256, 4, Epi, false, true>(tmA, W.tm[3], s, epi, st, pdl_now, &tmC, &tmR);
         return;
       }
     }

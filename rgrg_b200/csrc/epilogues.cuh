@@ -61,6 +61,19 @@ struct EpiStoreT {
   // the same with the bf16 residual of a full-width row segment added between bias and activation (the order of apply());
   // for the persistent kernel's TMA-store epilogue (gemm_tc.cuh), bf16 outputs only
   static constexpr bool kTmaOutRow = OUT_BF16 && (RES == RES_NONE || RES == RES_BF16);
+  static constexpr bool kResBf16 = (RES == RES_BF16);
+  template <int NV>
+  __device__ __forceinline__ void add_bias(int col0, float* o) const {
+    if constexpr (BIAS) add_vec_f32<NV>(o, bias + col0);
+  }
+  template <int NV>
+  __device__ __forceinline__ void activate(float* o) const {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      if constexpr (ACT == ACT_RELU) o[j] = fmaxf(o[j], 0.0f);
+      if constexpr (ACT == ACT_GELU_NEW) o[j] = gelu_new(o[j]);
+    }
+  }
   template <int NV>
   __device__ __forceinline__ void transform_row(int row, bool row_ok, int col0, float* o) const {
     if constexpr (BIAS) add_vec_f32<NV>(o, bias + col0);

@@ -197,7 +197,7 @@ struct SmemLayout {
   static constexpr bool kSlabs = (BN == 128 || BN == 256);
   static constexpr int STG_BYTES = EPI_WARPS * (kSlabs ? SLAB_BYTES : STG_FLOATS * 4);
   static constexpr int BAR_OFFSET = STG_OFFSET + STG_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + EPI_WARPS * 8 + 1024;  // + per-warp residual barriers + alignment slack
   static_assert(TOTAL <= 232448, "shared memory budget exceeded");
   static_assert(TOTAL > 116 * 1024, "must stay above half an SM's smem: exactly one CTA per SM may own TMEM");
 };
@@ -251,7 +251,7 @@ template <int BN, int STAGES>
 struct Pipe {
   using L = SmemLayout<BN, STAGES>;
   uint8_t* smem;
-  uint64_t *full_bar, *empty_bar, *tmem_full_bar, *tmem_empty_bar;
+  uint64_t *full_bar, *empty_bar, *tmem_full_bar, *tmem_empty_bar, *res_bar;
   uint32_t tmem_base;
 
   // barrier init + TMEM allocation; ends with a CTA-wide sync
@@ -262,6 +262,7 @@ struct Pipe {
     tmem_full_bar = empty_bar + STAGES;   // [2]
     tmem_empty_bar = tmem_full_bar + 2;   // [2]
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    res_bar = tmem_empty_bar + 4;         // [EPI_WARPS] residual slab landed (TMA-store epilogue with a bf16 residual)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
 #pragma unroll
@@ -269,6 +270,8 @@ struct Pipe {
         mbar_init(&full_bar[i], 1);
         mbar_init(&empty_bar[i], 1);
       }
+#pragma unroll
+      for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tmem_full_bar[i], 1);
@@ -374,19 +377,39 @@ struct Pipe {
     }
   }
 
+  // TMA-store epilogue with a bf16 residual: request slab `b` of the warp's part of tile `tc_` from the residual tensor ([M, N] bf16,
+  // same boxes as the output map) into the warp's slab, once the slab's previous store has been read out of it
+  __device__ __forceinline__ void res_fetch(const GemmShape& s, const TileCoord& tc_, const CUtensorMap* tmR, uint8_t* slab, int q, int half,
+                                            int b, int warp, int lane) const {
+    const int m0 = tc_.m_blk * BM + q * 32;
+    const int cs = tc_.n_blk * BN + half * (BN / 2) + b * 64;
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (m0 < s.M && cs < s.N) {
+        mbar_expect_tx(&res_bar[warp - 2], L::SLAB_BYTES);  // rows / columns out of bounds are zero-filled and still counted
+        tma_load_2d(slab, tmR, &res_bar[warp - 2], cs, m0);
+      }
+    }
+    __syncwarp();
+  }
   // epilogue main loop (warps 2..9, all lanes)
   template <class Epi, bool TMA_OUT>
-  __device__ __forceinline__ void epilogue(const GemmShape& s, const Epi& epi, int& it, long long* trace, const CUtensorMap* tmC) const {
+  __device__ __forceinline__ void epilogue(const GemmShape& s, const Epi& epi, int& it, long long* trace, const CUtensorMap* tmC,
+                                           const CUtensorMap* tmR) const {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q = warp & 3;            // TMEM lane quarter this warp may read: lanes [32q, 32q+32)
     const int half = (warp - 2) >> 2;  // which of the two warps of that quarter: takes 16-column chunks half, half+2, ...
     float* stg = reinterpret_cast<float*>(smem + L::STG_OFFSET) + (warp - 2) * STG_FLOATS;
     uint8_t* slab = smem + L::STG_OFFSET + (warp - 2) * L::SLAB_BYTES;  // TMA_OUT: this warp's 32-row x 128-byte store slab
+    uint32_t res_phase = 0;  // parity of the warp's residual barrier (one phase per fetched slab)
     const int nt = num_tiles(s);
     for (int tile = blockIdx.x; tile < nt; tile += gridDim.x, ++it) {
       const TileCoord tc_ = tile_coord(s, tile);
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
+      if constexpr (TMA_OUT) {
+        if constexpr (Epi::kResBf16) res_fetch(s, tc_, tmR, slab, q, half, 0, warp, lane);  // lands under the tile's main loop
+      }
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
       if (trace && warp == 2 && lane == 0 && tile == static_cast<int>(blockIdx.x)) trace[4] = clock64();
@@ -427,8 +450,13 @@ struct Pipe {
 #pragma unroll 1
         for (int b = 0; b < SLABS; ++b) {
           const int cs = tc_.n_blk * BN + half * COLS + b * 64;  // first output column of this slab
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the slab's previous store has read it
-          __syncwarp();
+          const bool live = m0 < s.M && cs < s.N;
+          if constexpr (Epi::kResBf16) {
+            if (b > 0) res_fetch(s, tc_, tmR, slab, q, half, b, warp, lane);  // slab 0's residual was requested before the accumulator wait
+          } else {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the slab's previous store has read it
+            __syncwarp();
+          }
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
             const int c = half * COLS + b * 64 + h2 * 32;
@@ -445,14 +473,33 @@ struct Pipe {
               float o[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
-              epi.template transform_row<32>(row, row_ok, cs + h2 * 32, o);
+              if constexpr (Epi::kResBf16) {
+                // acc + bias, + the residual row segment that TMA put into this lane's slab row, then the activation: apply()'s order
+                epi.template add_bias<32>(cs + h2 * 32, o);
+                if (live) {
+                  if (h2 == 0) {  // first read of the slab: its residual has landed (one phase per fetched slab)
+                    mbar_wait(&res_bar[warp - 2], res_phase);
+                    res_phase ^= 1;
+                  }
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    float rr[8];
+                    unpack8(*reinterpret_cast<const uint4*>(slab + lane * 128 + (((h2 * 4 + j) ^ sw) << 4)), rr);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o[8 * j + k] += rr[k];
+                  }
+                }
+                epi.template activate<32>(o);
+              } else {
+                epi.template transform_row<32>(row, row_ok, cs + h2 * 32, o);
+              }
 #pragma unroll
               for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(slab + lane * 128 + (((h2 * 4 + j) ^ sw) << 4)) = pack8(o + 8 * j);
             }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (lane == 0 && m0 < s.M && cs < s.N) {
+          if (lane == 0 && live) {
             asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmC)),
                          "r"(smem_u32(slab)), "r"(cs), "r"(m0)
                          : "memory");
@@ -523,6 +570,7 @@ template <int BN, int STAGES, class Epi, bool LN_HEAD = false, bool TMA_OUT = fa
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmC,
+                                                               const __grid_constant__ CUtensorMap tmR,
                                                                const GemmShape s, const Epi epi) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5;
@@ -558,7 +606,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   } else if (warp == 1) {
     if (lane == 0) pipe.mma(s, kbg, it, trace);
   } else {
-    pipe.template epilogue<Epi, TMA_OUT>(s, epi, it, trace, &tmC);
+    pipe.template epilogue<Epi, TMA_OUT>(s, epi, it, trace, &tmC, &tmR);
   }
   if (trace && warp == 2 && lane == 0) trace[5] = clock64();
   pipe.teardown();
@@ -623,7 +671,7 @@ inline int num_sms() {
 
 template <int BN, int STAGES, class Epi, bool LN_HEAD = false, bool TMA_OUT = false>
 inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s, const Epi& epi,
-                   cudaStream_t stream, bool pdl = false, const CUtensorMap* tmC = nullptr) {
+                   cudaStream_t stream, bool pdl = false, const CUtensorMap* tmC = nullptr, const CUtensorMap* tmR = nullptr) {
   using L = SmemLayout<BN, STAGES>;
   auto kern = gemm_tc_kernel<BN, STAGES, Epi, LN_HEAD, TMA_OUT>;
   if (TMA_OUT && !tmC) throw std::runtime_error("TMA-store epilogue needs the output tensor map");
@@ -658,7 +706,7 @@ inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmSha
   }
   cfg.attrs = attr;
   cfg.numAttrs = n;
-  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC ? *tmC : tmA, s, epi));
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC ? *tmC : tmA, tmR ? *tmR : tmA, s, epi));
 }
 
 // output map of the TMA-store epilogue: row-major bf16 [M, N]; slabs of 32 rows x 64 columns, 128B swizzle
