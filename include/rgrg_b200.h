@@ -178,8 +178,14 @@ RGRG_API int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst,
  *                             0 = c_attn GEMM (KV-append epilogue) + stand-alone attention kernel (always used by beam search)
  *   "gemm_2cta" (0/1)         decode projections through the CTA-pair kernel (256 x 256 tiles, each CTA stages half of W);
  *                             "gemm_2cta_waves" (1/2): used while the pair grid fits in this many waves (default 2)
- *   "epi_tma" (0/1)           CTA-pair kernel: plain epilogues leave through shared-memory slabs + TMA stores (1, default) or
- *                             through registers and 16-byte global stores (0); bit-identical
+ *                             "gemm_2cta_stages" (6/4/3): depth of its TMA ring
+ *   "epi_tma" (0/1)           tcgen05 GEMMs with a plain bf16 / fp32-partial epilogue (decode projections, 1x1 convolutions, fc6,
+ *                             fc7): results leave through shared-memory slabs + TMA stores (1, default) or through registers
+ *                             and 16-byte global stores (0); bit-identical
+ *   "attn_balance" (0/1)      fused attention: rows spread evenly over as many M tiles as the SMs hold (1, default) or 128-row tiles
+ *   "beam_fused_head" (0/1)   beam search: log-softmax + per-part top-k fused into the lm_head epilogue (1, default) or fp32 logits +
+ *                             separate top-k kernels
+ *   "roi_align_sep" (0/1)     separable RoIAlign kernel (1, default) or the direct one
  *   "attn_mc", "attn_early" (0/1)  fused attention: operand A shared between head pairs by TMA multicast / first K,V chunks
  *                             requested before the epilogue (both bit-identical, measured without gain, default 0)
  *   "trace" (0/1)             tuning only: %globaltimer stamps of the first / last CTA of the decode kernels

@@ -124,3 +124,15 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+(rgrg_oracle|beam_scorer|ref_harness|oracle)\b", text, re.M), f
+
+
+def test_every_engine_option_is_documented_in_the_header():
+    """rgrg_set_option keys accepted by the engine == keys described in include/rgrg_b200.h (the drop-in boundary's documentation)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    eng = open(os.path.join(root, "rgrg_b200", "csrc", "engine.cu")).read()
+    hdr = open(os.path.join(root, "include", "rgrg_b200.h")).read()
+    keys = set(re.findall(r'k == "([a-z0-9_]+)"', eng))
+    documented = set(re.findall(r'"([a-z0-9_]+)"', hdr))
+    assert keys, "option parser not found"
+    assert not (keys - documented), "undocumented options: %s" % sorted(keys - documented)
