@@ -182,6 +182,7 @@ RGRG_API int rgrg_debug_read(rgrg_engine_t* e, const char* name, void* host_dst,
  *   "epi_tma" (0/1)           tcgen05 GEMMs with a plain bf16 / fp32-partial epilogue (decode projections, 1x1 convolutions, fc6,
  *                             fc7): results leave through shared-memory slabs + TMA stores (1, default) or through registers
  *                             and 16-byte global stores (0); bit-identical
+ *                             "epi_tma_conv" (0/1): the same for the implicit 3x3 convolutions (4-D NHWC output boxes)
  *   "attn_balance" (0/1)      fused attention: rows spread evenly over as many M tiles as the SMs hold (1, default) or 128-row tiles
  *   "beam_fused_head" (0/1)   beam search: log-softmax + per-part top-k fused into the lm_head epilogue (1, default) or fp32 logits +
  *                             separate top-k kernels

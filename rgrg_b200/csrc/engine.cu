@@ -257,6 +257,7 @@ struct rgrg_engine {
   int opt_gemm_2cta_waves = 2;  // the pair kernel is used while its grid fits in this many waves (else the persistent 1-CTA kernel)
   int opt_attn_mc = 0;          // fused attention: head pairs (clusters of 2) share operand A through TMA multicast
   int opt_attn_early = 0;       // fused attention: request the first K / V chunks before the epilogue
+  int opt_epi_tma_conv = 1;     // ... also for the implicit 3x3 convolutions (4-D output boxes)
   int opt_epi_tma = 1;          // CTA-pair kernel: plain epilogues leave through shared-memory slabs + TMA stores
   int opt_gemm_2cta_stages = 6; // its TMA ring depth: 6 (one CTA per SM) / 4 / 3 (two CTAs per SM: prologue overlaps the predecessor's epilogue)
   int opt_gemm_2cta = 1;        // decode projections (c_proj / c_fc / mlp c_proj) through the CTA-pair kernel (gemm_2cta.cuh)
@@ -491,8 +492,10 @@ struct rgrg_engine {
   void launch_bn(int bn, const CUtensorMap& tmA, const Linear& W, const tc::GemmShape& s, const Epi& epi, cudaStream_t st) {
     // plain GEMMs with a bf16 output (1x1 convolutions, fc6 / fc7): TMA-store epilogue (gemm_tc.cuh)
     if constexpr (TmaOutRowOk<Epi>::value) {
-      if (opt_epi_tma && !s.conv && s.k_splits <= 1 && (bn == 128 || bn == 256) && epi.ldc == s.N && s.N % 64 == 0) {
-        const CUtensorMap tmC = tc::make_tmap_out_bf16(epi.out, s.M, s.N);
+      const bool conv_ok = !s.conv || (!Epi::kResBf16 && opt_epi_tma_conv);  // implicit conv: 4-D NHWC output boxes, no residual variant
+      if (opt_epi_tma && conv_ok && s.k_splits <= 1 && (bn == 128 || bn == 256) && epi.ldc == s.N && s.N % 64 == 0) {
+        const CUtensorMap tmC = s.conv ? tc::make_tmap_out_nhwc(epi.out, s.M / (static_cast<uint64_t>(s.H) * s.W), s.H, s.W, s.N)
+                                       : tc::make_tmap_out_bf16(epi.out, s.M, s.N);
         CUtensorMap tmR = tmC;  // the bf16 residual, if any, comes in through the same boxes
         if constexpr (Epi::kResBf16) tmR = tc::make_tmap_out_bf16(epi.res, s.M, s.N);
         if (bn == 128) tc::launch<128, 6, Epi, false, true>(tmA, W.tm[1], s, epi, st, pdl_now, &tmC, &tmR);
@@ -2053,6 +2056,7 @@ int rgrg_set_option(rgrg_engine_t* e, const char* key, int value) {
   else if (k == "gemm_2cta") e->opt_gemm_2cta = value;
   else if (k == "gemm_2cta_stages") e->opt_gemm_2cta_stages = value;
   else if (k == "epi_tma") e->opt_epi_tma = value;
+  else if (k == "epi_tma_conv") e->opt_epi_tma_conv = value;
   else if (k == "attn_early") e->opt_attn_early = value;
   else if (k == "attn_mc") e->opt_attn_mc = value;
   else if (k == "gemm_2cta_waves") e->opt_gemm_2cta_waves = value;

@@ -442,10 +442,12 @@ struct Pipe {
         constexpr int COLS = BN / 2;        // two warps per TMEM lane quarter, half of the tile's columns each
         constexpr int SLABS = COLS / 64;
         static_assert(L::kSlabs && COLS % 64 == 0, "TMA-store epilogue needs BN = 128 or 256");
+        // implicit-conv tiles are 8 x 16 pixel patches: the warp's 32 rows are 2 image rows x 16 pixels -> one 4-D box of the NHWC
+        // output map (every conv tile is full); plain GEMM: 32 consecutive rows of [M, N]
         const int r = q * 32 + lane;
         const int row = tc_.m_blk * BM + r;
-        const bool row_ok = row < s.M;
-        const int m0 = tc_.m_blk * BM + q * 32;
+        const bool row_ok = !s.conv && row < s.M;
+        const int m0 = s.conv ? 0 : tc_.m_blk * BM + q * 32;
         const int sw = lane & 7;
 #pragma unroll 1
         for (int b = 0; b < SLABS; ++b) {
@@ -500,9 +502,15 @@ struct Pipe {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0 && live) {
-            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmC)),
-                         "r"(smem_u32(slab)), "r"(cs), "r"(m0)
-                         : "memory");
+            if (s.conv)
+              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                               reinterpret_cast<uint64_t>(tmC)),
+                           "r"(smem_u32(slab)), "r"(cs), "r"(tc_.w0), "r"(tc_.h0 + 2 * q), "r"(tc_.img)
+                           : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmC)),
+                           "r"(smem_u32(slab)), "r"(cs), "r"(m0)
+                           : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
@@ -709,6 +717,19 @@ inline void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmSha
   CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC ? *tmC : tmA, tmR ? *tmR : tmA, s, epi));
 }
 
+// output map of the TMA-store epilogue in implicit-conv mode: NHWC bf16; a warp's slab = 64 channels x 16 (W) x 2 (H) x 1 image
+inline CUtensorMap make_tmap_out_nhwc(const void* ptr, uint64_t N, uint64_t H, uint64_t W, uint64_t C) {
+  CUtensorMap m;
+  cuuint64_t dims[4] = {C, W, H, N};
+  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {64, 16, 2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(out nhwc) failed: " + std::to_string((int)r));
+  return m;
+}
 // output map of the TMA-store epilogue: row-major bf16 [M, N]; slabs of 32 rows x 64 columns, 128B swizzle
 inline CUtensorMap make_tmap_out_bf16(const void* ptr, uint64_t M, uint64_t N) {
   CUtensorMap m;
