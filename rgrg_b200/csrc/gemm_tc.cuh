@@ -245,6 +245,10 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmShape& s, int tile) {
 //                 (lane = row) -> swizzled smem transpose -> 8 consecutive columns per lane -> fused epilogue functor
 //                 with 16-byte coalesced global accesses.  (One warp per scheduler cannot hide its own latency: the
 //                 4-warp version of this epilogue needed 14 us for a 128x192 tile, 3x the tile's MMA time.)
+//                 TMA_OUT variant (plain bf16-output GEMMs and implicit convs at BN = 128 / 256): lane = row all the way —
+//                 bias / residual / activation in registers, bf16 rows into the warp's 128B-swizzled 4 KB slab, one
+//                 cp.async.bulk.tensor store per 32 rows x 64 columns; a bf16 residual is fetched by TMA into the same slab
+//                 before the accumulator wait.  The register variant is bound by store issue where K is short.
 // Ring-slot and accumulator-stage counters (kbg, it) are carried by the caller.
 // ---------------------------------------------------------------------------------------------------------------
 template <int BN, int STAGES>
